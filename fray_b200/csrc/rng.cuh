@@ -1,0 +1,110 @@
+// rng.cuh -- counter-based per-pixel random numbers (product implementation).
+//
+// Replaces the reference's thread-id keyed std::mt19937 table (/root/reference/src/random_generator.cpp:31-131),
+// whose streams are not reproducible. A stream is a pure function of (seed, pixel, sample, branch) and the
+// index of the draw, so the GPU, the host and the CPU checkers see identical sample sequences no matter how
+// work is scheduled. The stream layout and the mapping of Random::randfloat / randdouble / randint /
+// unitDiscSample (src/random_generator.cpp:41-80) onto 32-bit draws is specified in DESIGN.md "RNG contract";
+// tests/test_rng.py checks this file draw for draw against the independently written oracle/fray_rng.h.
+//
+// Usable from host code too (the .fray parser's randfloat()/randint() macros, src/scene.cpp:609-653).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FRAY_HD __host__ __device__ __forceinline__
+#else
+#define FRAY_HD inline
+#endif
+
+namespace fray {
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+FRAY_HD uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+	return __umulhi(a, b);
+#else
+	return (uint32_t) (((uint64_t) a * b) >> 32);
+#endif
+}
+
+// Philox-4x32 with 10 rounds (Salmon, Moraes, Dror, Shaw, SC'11); key schedule bumps after every round.
+FRAY_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+	for (int round = 0; round < 10; round++) {
+		const uint32_t lo0 = 0xD2511F53u * c0, hi0 = mulhi32(0xD2511F53u, c0);
+		const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = mulhi32(0xCD9E8D57u, c2);
+		c0 = hi1 ^ c1 ^ k0;
+		c1 = lo1;
+		c2 = hi0 ^ c3 ^ k1;
+		c3 = lo0;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	return Philox4{ c0, c1, c2, c3 };
+}
+
+FRAY_HD uint32_t rngMix(uint32_t v)
+{
+	v = (v ^ (v >> 16)) * 0x7FEB352Du;
+	v = (v ^ (v >> 15)) * 0x846CA68Bu;
+	return v ^ (v >> 16);
+}
+
+// stream id of the k-th secondary ray a Whitted shader spawns after `draws` numbers were consumed
+FRAY_HD uint32_t rngChildBranch(uint32_t branch, uint32_t draws, uint32_t k)
+{
+	return rngMix(branch ^ rngMix(draws * 0x9E3779B9u + k + 1u)) | 1u;
+}
+
+struct Rng {
+	uint32_t seed, pixel, sample, branch;
+	uint32_t count; // draws consumed
+	Philox4 blk;    // block ((count - 1) >> 2) when count & 3
+
+	FRAY_HD void init(uint32_t seed_, uint32_t pixel_, uint32_t sample_, uint32_t branch_)
+	{
+		seed = seed_; pixel = pixel_; sample = sample_; branch = branch_; count = 0;
+	}
+	FRAY_HD void refill() { blk = philox4x32_10(count >> 2, pixel, sample, branch, seed, 0x46524159u); }
+	FRAY_HD uint32_t next()
+	{
+		const uint32_t lane = count & 3u;
+		if (lane == 0) refill();
+		count++;
+		return lane == 0 ? blk.x : (lane == 1 ? blk.y : (lane == 2 ? blk.z : blk.w));
+	}
+	// advance without generating (the discarded first spawnRay of pathtrace, src/main.cpp:219-224)
+	FRAY_HD void skip(uint32_t n)
+	{
+		const uint32_t target = count + n;
+		count = target & ~3u;
+		if (target & 3u) refill();
+		count = target;
+	}
+	FRAY_HD float randfloat() { return (float) (next() >> 8) * (1.0f / 16777216.0f); }
+	FRAY_HD double randdouble()
+	{
+		const uint64_t lo = next();
+		const uint64_t hi = next();
+		return (double) (((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+	}
+	// single-precision view of randdouble(): consumes the same two draws
+	FRAY_HD float randdoubleAsFloat()
+	{
+		next();
+		return (float) (next() >> 8) * (1.0f / 16777216.0f);
+	}
+	FRAY_HD int randint(int a, int b)
+	{
+		const uint32_t n = (uint32_t) (b - a + 1);
+		return a + (int) mulhi32(next(), n);
+	}
+};
+
+} // namespace fray
