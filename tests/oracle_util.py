@@ -1,0 +1,130 @@
+"""Test-side access to the CPU checkers under oracle/ (never imported by the product).
+
+* ``oracle_render``      -- our FP64 restatement (oracle/libfray_oracle.so) on a flattened scene
+* ``reference_render``   -- the real reference code with the counter RNG (oracle/_ref/fray_ref_ctr)
+* ``override_scene``     -- write a variant of a bundled scene with changed GlobalSettings / Camera properties
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+import fray_b200 as fb
+
+ROOT = fb.REPO_ROOT
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+DATA_DIR = os.environ.get("FRAY_DATA", os.path.join(REF_DIR, "data"))
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+REF_CTR = os.path.join(REF_DIR, "fray_ref_ctr")
+REF_BIN = os.path.join(REF_DIR, "fray_ref")
+
+_oracle = None
+
+
+def oracle_lib() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "libfray_oracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"])
+        L = C.CDLL(path)
+        L.fray_oracle_render.argtypes = [C.c_void_p, C.POINTER(fb.FrayFrame), C.c_void_p, C.POINTER(fb.FrayStats), C.c_int]
+        L.fray_oracle_samples_per_pixel.argtypes = [C.c_void_p]
+        L.fray_oracle_rng_draws.argtypes = [C.c_uint32] * 4 + [C.c_int, C.c_void_p]
+        L.fray_oracle_rng_child.restype = C.c_uint32
+        L.fray_oracle_rng_child.argtypes = [C.c_uint32] * 3
+        L.fray_oracle_philox.argtypes = [C.c_void_p] * 3
+        L.fray_oracle_screen_ray.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.fray_oracle_intersect.argtypes = [C.c_void_p] * 4
+        L.fray_oracle_environment.argtypes = [C.c_void_p] * 3
+        _oracle = L
+    return _oracle
+
+
+def oracle_render(scene: fb.Scene, threads: int = 0, **frame_kw):
+    """Render `scene` with the FP64 restatement; same frame semantics as GpuContext.render."""
+    L = oracle_lib()
+    out = np.empty((scene.height, scene.width, 3), dtype=np.float32)
+    frame = fb.make_frame(**frame_kw)
+    stats = fb.FrayStats()
+    rc = L.fray_oracle_render(scene.flat, C.byref(frame), out.ctypes.data, C.byref(stats), threads)
+    if rc != 0:
+        raise RuntimeError("fray_oracle_render failed")
+    return out, fb.RenderStats.of(stats)
+
+
+def read_dump(path: str) -> np.ndarray:
+    with open(path, "rb") as f:
+        w, h = np.fromfile(f, np.int32, 2)
+        return np.fromfile(f, np.float32, int(w) * int(h) * 3).reshape(int(h), int(w), 3)
+
+
+def read_aov(path: str):
+    with open(path, "rb") as f:
+        w, h = np.fromfile(f, np.int32, 2)
+        rec = np.fromfile(f, np.dtype([("node", "<i4"), ("dist", "<f8")]), int(w) * int(h))
+    return rec["node"].reshape(int(h), int(w)), rec["dist"].reshape(int(h), int(w))
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_CTR) and os.path.isdir(DATA_DIR)
+
+
+def scene_path(name: str) -> str:
+    """'cornell_box' or 'hw9/dragon' -> path of the bundled .fray file in the data mirror."""
+    return os.path.join(DATA_DIR, name + ".fray")
+
+
+_BLOCK_RE = {"GlobalSettings": re.compile(r"^\s*GlobalSettings\b[^{]*\{", re.M), "Camera": re.compile(r"^\s*Camera\b[^{]*\{", re.M)}
+
+
+def override_scene(name: str, tag: str, settings: dict | None = None, camera: dict | None = None) -> str:
+    """Write `<name>__<tag>.fray` beside the original (asset paths are relative to the scene file,
+    /root/reference/src/scene.cpp:710-721) with the given properties put FIRST in the block, so they win
+    (ParsedBlockImpl::findProperty returns the first match, src/scene.cpp:112-122)."""
+    src = scene_path(name)
+    text = open(src).read()
+    for block, props in (("GlobalSettings", settings), ("Camera", camera)):
+        if not props:
+            continue
+        m = _BLOCK_RE[block].search(text)
+        if not m:
+            raise RuntimeError(f"{src} has no {block} block")
+        ins = "".join(f"\n\t{k} {v}" for k, v in props.items())
+        text = text[:m.end()] + ins + text[m.end():]
+    dst = os.path.join(os.path.dirname(src), f"{os.path.basename(name)}__{tag}.fray")
+    with open(dst, "w") as f:
+        f.write(text)
+    return dst
+
+
+def reference_render(scene_file: str, seed: int = 42, threads: int = 0, aov: bool = False):
+    """Run the real reference code on the counter-RNG contract. Returns (rgb, seconds[, node, dist])."""
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "out.f32")
+        cmd = [REF_CTR, scene_file, out, "--seed", str(seed)]
+        if threads:
+            cmd += ["--threads", str(threads)]
+        if aov:
+            cmd += ["--aov", os.path.join(td, "out.aov")]
+        txt = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+        m = re.search(r"Render took ([0-9.]+)s", txt)
+        sec = float(m.group(1)) if m else float("nan")
+        rgb = read_dump(out)
+        if aov:
+            node, dist = read_aov(os.path.join(td, "out.aov"))
+            return rgb, sec, node, dist
+        return rgb, sec
+
+
+def compare(a: np.ndarray, b: np.ndarray, tol: float = 1e-3):
+    """(fraction of pixels whose max channel difference <= tol, RMSE, max abs difference)."""
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    per_px = d.max(axis=-1)
+    return float((per_px <= tol).mean()), float(np.sqrt((d ** 2).mean())), float(per_px.max())
