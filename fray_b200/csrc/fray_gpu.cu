@@ -1,0 +1,355 @@
+// fray_gpu.cu -- context management and the C ABI of libfray_gpu.so (include/fray_gpu.h).
+//
+// The context owns every device allocation: the scene image (one blob, see scene_image.h), the bucket list of the
+// current call, the work counter / ray counters, a device framebuffer and a pinned host staging buffer for
+// fray_gpu_render(). One CUDA stream per context; kernel time is measured with CUDA events on that stream.
+// There is no CPU code path: if CUDA is unavailable every entry point fails with FRAY_GPU_ENODEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "render_kernels.cuh"
+#include "scene_image.h"
+
+using namespace fray;
+
+static thread_local std::string g_lastError;
+
+static int fail(int code, const std::string& msg)
+{
+	g_lastError = msg;
+	return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+	do {                                                                                                 \
+		cudaError_t e_ = (expr);                                                                         \
+		if (e_ != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+struct FrayGpuCtx {
+	int device = 0;
+	int precision = FRAY_GPU_FP32;
+	int features = 0;
+	int width = 0, height = 0;
+	int defaultSpp = 1;
+	int numSMs = 0;
+	SceneImage<float> img32;
+	SceneImage<double> img64;
+	DScene<float> sc32;
+	DScene<double> sc64;
+	void* dBlob = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	int4* dBuckets = nullptr;
+	int bucketCapacity = 0;
+	unsigned long long* dCounters = nullptr; // 3 counters
+	unsigned int* dWork = nullptr;
+	int* dError = nullptr;
+	float* dFrame = nullptr;     // own framebuffer for fray_gpu_render
+	float* hStaging = nullptr;   // pinned
+	int occGI = -1, occWhitted = -1;
+	bool pendingStats = false;
+	int launches = 0;
+	cudaStream_t lastStream = nullptr;
+};
+
+// d_rgb[i] = d_sum[i] / spp  (`avg / samplesPerPixel`, src/main.cpp:360)
+__global__ void resolveKernel(const float* __restrict__ sum, float* __restrict__ rgb, size_t n, float spp)
+{
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) rgb[i] = sum[i] / spp;
+}
+
+template <typename R> static void convertCamera(DCamera<R>& d, const FrayGpuCamera& cam)
+{
+	for (int i = 0; i < 3; i++) {
+		d.pos[i] = (R) cam.pos[i]; d.topLeft[i] = (R) cam.top_left[i]; d.topRight[i] = (R) cam.top_right[i];
+		d.bottomLeft[i] = (R) cam.bottom_left[i]; d.front[i] = (R) cam.front[i]; d.up[i] = (R) cam.up[i]; d.right[i] = (R) cam.right[i];
+		d.leftMask[i] = cam.left_mask[i]; d.rightMask[i] = cam.right_mask[i];
+	}
+	d.w = (R) cam.w; d.h = (R) cam.h; d.aperture = (R) cam.aperture_size; d.focalDist = (R) cam.focal_plane_dist;
+	d.stereoSep = (R) cam.stereo_separation; d.dof = cam.dof;
+}
+
+extern "C" {
+
+uint32_t fray_gpu_abi_version(void) { return FRAY_GPU_ABI_VERSION; }
+
+const char* fray_gpu_last_error(void) { return g_lastError.c_str(); }
+
+int fray_gpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int fray_gpu_samples_per_pixel(const FrayGpuScene* scene) { return scene ? samplesPerPixel(*scene) : 0; }
+
+void fray_gpu_destroy(FrayGpuCtx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	cudaFree(c->dBlob);
+	cudaFree(c->dBuckets);
+	cudaFree(c->dCounters);
+	cudaFree(c->dWork);
+	cudaFree(c->dError);
+	cudaFree(c->dFrame);
+	if (c->hStaging) cudaFreeHost(c->hStaging);
+	if (c->evStart) cudaEventDestroy(c->evStart);
+	if (c->evStop) cudaEventDestroy(c->evStop);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int fray_gpu_create(const FrayGpuScene* scene, int device, int precision, FrayGpuCtx** out)
+{
+	if (!scene || !out) return fail(FRAY_GPU_EINVAL, "null argument");
+	*out = nullptr;
+	if (precision != FRAY_GPU_FP32 && precision != FRAY_GPU_FP64) return fail(FRAY_GPU_EINVAL, "precision must be FRAY_GPU_FP32 or FRAY_GPU_FP64");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(FRAY_GPU_ENODEVICE, std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+		                                    "); libfray_gpu has no CPU fallback");
+	}
+	if (device < 0 || device >= ndev) return fail(FRAY_GPU_EINVAL, "device ordinal out of range");
+
+	FrayGpuCtx* c = new FrayGpuCtx;
+	c->device = device;
+	c->precision = precision;
+	c->width = scene->settings.frame_width;
+	c->height = scene->settings.frame_height;
+	c->defaultSpp = samplesPerPixel(*scene);
+	std::string err;
+	const bool ok = precision == FRAY_GPU_FP32 ? c->img32.build(*scene, err) : c->img64.build(*scene, err);
+	if (!ok) {
+		delete c;
+		return fail(FRAY_GPU_EINVAL, err);
+	}
+	c->features = precision == FRAY_GPU_FP32 ? c->img32.features : c->img64.features;
+	const std::vector<unsigned char>& blob = precision == FRAY_GPU_FP32 ? c->img32.blob : c->img64.blob;
+
+#define CREATE_TRY(expr)                                                                   \
+	do {                                                                                   \
+		cudaError_t e_ = (expr);                                                           \
+		if (e_ != cudaSuccess) {                                                           \
+			std::string m_ = std::string(#expr) + ": " + cudaGetErrorString(e_);           \
+			fray_gpu_destroy(c);                                                           \
+			return fail(FRAY_GPU_ECUDA, m_);                                               \
+		}                                                                                  \
+	} while (0)
+	CREATE_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+	c->numSMs = prop.multiProcessorCount;
+	CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaEventCreate(&c->evStart));
+	CREATE_TRY(cudaEventCreate(&c->evStop));
+	CREATE_TRY(cudaMalloc(&c->dBlob, blob.size()));
+	CREATE_TRY(cudaMemcpyAsync(c->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+	CREATE_TRY(cudaMalloc(&c->dCounters, 3 * sizeof(unsigned long long)));
+	CREATE_TRY(cudaMalloc(&c->dWork, sizeof(unsigned int)));
+	CREATE_TRY(cudaMalloc(&c->dError, sizeof(int)));
+	CREATE_TRY(cudaMemsetAsync(c->dError, 0, sizeof(int), c->stream));
+	const size_t frameBytes = (size_t) c->width * c->height * 3 * sizeof(float);
+	CREATE_TRY(cudaMalloc(&c->dFrame, frameBytes));
+	CREATE_TRY(cudaMallocHost(&c->hStaging, frameBytes));
+	CREATE_TRY(cudaStreamSynchronize(c->stream));
+#undef CREATE_TRY
+	if (precision == FRAY_GPU_FP32) c->sc32 = c->img32.bind(c->dBlob);
+	else c->sc64 = c->img64.bind(c->dBlob);
+	*out = c;
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_update_camera(FrayGpuCtx* c, const FrayGpuCamera* cam)
+{
+	if (!c || !cam) return fail(FRAY_GPU_EINVAL, "null argument");
+	// the camera travels as a kernel parameter (constant bank), so a per-frame update costs no device copy
+	if (c->precision == FRAY_GPU_FP32) convertCamera(c->sc32.cam, *cam); else convertCamera(c->sc64.cam, *cam);
+	if ((int) cam->w != c->width || (int) cam->h != c->height) return fail(FRAY_GPU_EINVAL, "frame size cannot change without re-creating the context");
+	return FRAY_GPU_OK;
+}
+
+// serpentine bucket list, src/sdl.cpp:243-262
+static void bucketList(int W, int H, std::vector<int4>& out)
+{
+	const int B = FRAY_BUCKET;
+	const int BW = (W - 1) / B + 1, BH = (H - 1) / B + 1;
+	out.clear();
+	for (int y = 0; y < BH; y++)
+		for (int i = 0; i < BW; i++) {
+			const int x = (y % 2 == 0) ? i : BW - 1 - i;
+			int4 r;
+			r.x = x * B;
+			r.y = y * B;
+			r.z = (x + 1) * B < W ? B : W - x * B;
+			r.w = (y + 1) * B < H ? B : H - y * B;
+			out.push_back(r);
+		}
+}
+
+static int pow2Floor(int v)
+{
+	int p = 1;
+	while (p * 2 <= v) p *= 2;
+	return p;
+}
+
+static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStream_t stream, bool timed)
+{
+	if (!c || !f || !dOut) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	const bool gi = c->precision == FRAY_GPU_FP32 ? c->sc32.gi : c->sc64.gi;
+	const bool randomOffsets = gi || (c->precision == FRAY_GPU_FP32 ? c->sc32.cam.dof : c->sc64.cam.dof);
+	const int spp = f->spp > 0 ? f->spp : c->defaultSpp;
+	int s0 = f->sample_begin, s1 = f->sample_end;
+	if (s0 == 0 && s1 == 0) s1 = spp;
+	if (s0 < 0 || s1 < s0 || s1 > spp) return fail(FRAY_GPU_EINVAL, "sample range outside [0, spp]");
+	if (!randomOffsets && spp > 5) return fail(FRAY_GPU_EINVAL, "more than 5 samples need dof or gi (fixed AA table has 5 entries, src/main.cpp:55-61)");
+	if (f->mode != FRAY_RENDER_BEAUTY && f->mode != FRAY_RENDER_AOV) return fail(FRAY_GPU_EINVAL, "unknown render mode");
+	const int bcount = f->bucket_count > 0 ? f->bucket_count : 1;
+	const int brank = f->bucket_count > 0 ? f->bucket_rank : 0;
+	if (brank < 0 || brank >= bcount) return fail(FRAY_GPU_EINVAL, "bucket_rank outside [0, bucket_count)");
+
+	std::vector<int4> all, owned;
+	bucketList(c->width, c->height, all);
+	for (size_t i = 0; i < all.size(); i++)
+		if ((int) (i % bcount) == brank) owned.push_back(all[i]);
+	if ((int) owned.size() > c->bucketCapacity) {
+		cudaFree(c->dBuckets);
+		c->dBuckets = nullptr;
+		c->bucketCapacity = 0;
+		CUDA_TRY(cudaMalloc(&c->dBuckets, all.size() * sizeof(int4)));
+		c->bucketCapacity = (int) all.size();
+	}
+
+	RenderParams p;
+	memset(&p, 0, sizeof(p));
+	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
+	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
+	const int G = std::min(32, pow2Floor(std::max(1, s1 - s0)));
+	p.lanesPerPixel = G;
+	const int P = 32 / G; // pixels per warp task: 32 -> 8x4, 16 -> 4x4, 8 -> 4x2, 4 -> 2x2, 2 -> 2x1, 1 -> 1x1
+	p.tileW = P >= 32 ? 8 : (P >= 8 ? 4 : (P >= 2 ? 2 : 1));
+	p.tileH = P / p.tileW;
+	p.numBuckets = (int) owned.size();
+	p.buckets = c->dBuckets;
+	p.totalTasks = p.numBuckets * (FRAY_BUCKET / p.tileW) * (FRAY_BUCKET / p.tileH);
+	p.out = dOut;
+	p.counters = c->dCounters;
+	p.workCounter = c->dWork;
+	p.errorFlag = c->dError;
+
+	if (owned.size() != all.size()) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
+	if (!owned.empty()) CUDA_TRY(cudaMemcpyAsync(c->dBuckets, owned.data(), owned.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemsetAsync(c->dCounters, 0, 3 * sizeof(unsigned long long), stream));
+	CUDA_TRY(cudaMemsetAsync(c->dWork, 0, sizeof(unsigned int), stream));
+
+	int& occ = gi ? c->occGI : c->occWhitted;
+	if (occ < 0) {
+		occ = c->precision == FRAY_GPU_FP32 ? renderOccupancy<float>(c->features, gi) : renderOccupancy<double>(c->features, gi);
+		if (occ < 1) occ = 1;
+	}
+	LaunchConfig cfg;
+	cfg.stream = stream;
+	cfg.gridBlocks = c->numSMs * occ; // persistent: every resident CTA slot of the chip, exactly once
+	if (f->mode == FRAY_RENDER_AOV) cfg.gridBlocks = c->numSMs * 8;
+	c->launches = 0;
+	if (timed) CUDA_TRY(cudaEventRecord(c->evStart, stream));
+	if (p.totalTasks > 0 && (s1 > s0 || f->mode == FRAY_RENDER_AOV)) {
+		cudaError_t e = c->precision == FRAY_GPU_FP32 ? launchRender<float>(c->sc32, p, c->features, f->mode, cfg)
+		                                                : launchRender<double>(c->sc64, p, c->features, f->mode, cfg);
+		if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+		c->launches = 1;
+	} else if (owned.size() == all.size()) {
+		CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
+	}
+	if (timed) CUDA_TRY(cudaEventRecord(c->evStop, stream));
+	c->pendingStats = timed;
+	c->lastStream = stream;
+	return FRAY_GPU_OK;
+}
+
+static int fetchStats(FrayGpuCtx* c, FrayGpuStats* stats)
+{
+	CUDA_TRY(cudaStreamSynchronize(c->lastStream ? c->lastStream : c->stream));
+	unsigned long long h[3] = { 0, 0, 0 };
+	int err = 0;
+	CUDA_TRY(cudaMemcpy(h, c->dCounters, sizeof(h), cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemcpy(&err, c->dError, sizeof(int), cudaMemcpyDeviceToHost));
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		stats->rays = h[0];
+		stats->primary_rays = h[1];
+		stats->shadow_rays = h[2];
+		stats->kernel_launches = c->launches;
+		if (c->pendingStats) {
+			float ms = 0;
+			CUDA_TRY(cudaEventElapsedTime(&ms, c->evStart, c->evStop));
+			stats->device_ms = ms;
+		}
+	}
+	if (err) {
+		cudaMemset(c->dError, 0, sizeof(int));
+		return fail(FRAY_GPU_EUNSUPPORTED, "device ray-task stack overflow (too many pending secondary rays)");
+	}
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_render(FrayGpuCtx* c, const FrayGpuFrame* frame, float* rgb_out, FrayGpuStats* stats)
+{
+	if (!c || !frame || !rgb_out) return fail(FRAY_GPU_EINVAL, "null argument");
+	int rc = renderInto(c, frame, c->dFrame, c->stream, true);
+	if (rc != FRAY_GPU_OK) return rc;
+	const size_t bytes = (size_t) c->width * c->height * 3 * sizeof(float);
+	// straight into the caller's buffer when it is page-locked (e.g. a pinned torch tensor), else through our pinned staging buffer
+	cudaPointerAttributes attr;
+	bool pinned = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (pinned) {
+		CUDA_TRY(cudaMemcpyAsync(rgb_out, c->dFrame, bytes, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+	} else {
+		CUDA_TRY(cudaMemcpyAsync(c->hStaging, c->dFrame, bytes, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		memcpy(rgb_out, c->hStaging, bytes);
+	}
+	return fetchStats(c, stats);
+}
+
+int fray_gpu_render_device(FrayGpuCtx* c, const FrayGpuFrame* frame, void* d_rgb, void* cuda_stream)
+{
+	if (!c) return fail(FRAY_GPU_EINVAL, "null argument");
+	return renderInto(c, frame, (float*) d_rgb, cuda_stream ? (cudaStream_t) cuda_stream : c->stream, true);
+}
+
+int fray_gpu_resolve_device(FrayGpuCtx* c, const void* d_sum, void* d_rgb, int32_t spp, void* cuda_stream)
+{
+	if (!c || !d_sum || !d_rgb || spp < 1) return fail(FRAY_GPU_EINVAL, "bad argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	const size_t n = (size_t) c->width * c->height * 3;
+	cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : c->stream;
+	resolveKernel<<<c->numSMs * 4, 256, 0, st>>>((const float*) d_sum, (float*) d_rgb, n, (float) spp);
+	CUDA_TRY(cudaGetLastError());
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_sync(FrayGpuCtx* c, FrayGpuStats* stats)
+{
+	if (!c) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	return fetchStats(c, stats);
+}
+
+} // extern "C"

@@ -13,8 +13,19 @@
 
 #if defined(__CUDACC__)
 #define FRAY_HD __host__ __device__ __forceinline__
+// large, rarely executed or multiply-referenced routines: one out-of-line copy per kernel keeps code size and
+// compile time in check (CSG evaluation, the direct-lighting loop shared by all Whitted shader levels)
+#define FRAY_HD_COLD __host__ __device__ __noinline__
+// hot routines: inlined in the fast-precision unit; the parity unit (render_fp64.cu) trades speed for compile time
+#if defined(FRAY_PARITY_UNIT)
+#define FRAY_HD_HOT __host__ __device__ __noinline__
+#else
+#define FRAY_HD_HOT __host__ __device__ __forceinline__
+#endif
 #else
 #define FRAY_HD inline
+#define FRAY_HD_COLD inline
+#define FRAY_HD_HOT inline
 #endif
 
 namespace fray {

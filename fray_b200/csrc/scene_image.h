@@ -1,0 +1,332 @@
+// scene_image.h -- builds the device-layout image of a scene from the C-ABI tables (include/fray_gpu.h).
+//
+// Host-side, plain C++. The image is ONE contiguous blob (16-byte aligned sections) plus a DScene<R> whose pointers
+// are offsets into it; fray_gpu.cu copies the blob to HBM with a single cudaMemcpy and rebases the pointers.
+// Conversions done here, once per scene:
+//   * FP64 tables -> R (float for the fast path, double for the parity path)
+//   * per-triangle vertex A gathered (the reference indexes vertices[T.v[0]] on every test, src/mesh.cpp:107)
+//   * KD node boxes: the reference re-derives each child box by splitting the parent's while descending
+//     (src/mesh.cpp:371-373, src/bbox.h:205-211); the same boxes are materialised per node here
+//   * relative indices -> absolute, identity transforms flagged, "does anything on this node read (u,v)" flagged
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "core.cuh"
+
+namespace fray {
+
+template <typename R> struct SceneImage {
+	std::vector<unsigned char> blob;
+	DScene<R> offsets; // pointer members hold byte offsets into blob
+	int features = 0;  // FRAY_F_* needed by this scene
+
+	template <typename T> size_t append(const std::vector<T>& v)
+	{
+		size_t off = (blob.size() + 15) & ~(size_t) 15;
+		blob.resize(off + v.size() * sizeof(T) + 16, 0); // never empty: a null offset means "first table"
+		if (!v.empty()) memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+		return off;
+	}
+
+	static void cvt3(R* dst, const double* src) { dst[0] = (R) src[0]; dst[1] = (R) src[1]; dst[2] = (R) src[2]; }
+	static void cvtXform(DXform<R>& o, const FrayGpuTransform& t)
+	{
+		bool ident = true;
+		for (int i = 0; i < 9; i++) {
+			o.m[i] = (R) t.m[i];
+			o.inv[i] = (R) t.inv[i];
+			const double e = (i % 4 == 0) ? 1.0 : 0.0;
+			if (t.m[i] != e || t.inv[i] != e) ident = false;
+		}
+		for (int i = 0; i < 3; i++) {
+			o.off[i] = (R) t.offset[i];
+			if (t.offset[i] != 0) ident = false;
+		}
+		o.identity = ident;
+	}
+
+	static bool textureReadsUV(const FrayGpuScene& s, int ti)
+	{
+		if (ti < 0) return false;
+		int t = s.textures[ti].type;
+		return t == FRAY_TEX_CHECKER || t == FRAY_TEX_BITMAP || t == FRAY_TEX_BUMP;
+	}
+	static bool shaderReadsUV(const FrayGpuScene& s, int si, int depth)
+	{
+		if (si < 0 || depth > 8) return false;
+		const FrayGpuShader& sh = s.shaders[si];
+		if (textureReadsUV(s, sh.texture)) return true;
+		if (sh.type == FRAY_SHADER_LAYERED)
+			for (int i = 0; i < sh.num_layers; i++) {
+				const FrayGpuLayer& L = s.layers[sh.first_layer + i];
+				if (textureReadsUV(s, L.texture) || shaderReadsUV(s, L.shader, depth + 1)) return true;
+			}
+		return false;
+	}
+	static int layeredDepth(const FrayGpuScene& s, int si, int depth)
+	{
+		if (depth > 8) return 99;
+		const FrayGpuShader& sh = s.shaders[si];
+		if (sh.type != FRAY_SHADER_LAYERED) return 0;
+		int d = 0;
+		for (int i = 0; i < sh.num_layers; i++) d = std::max(d, layeredDepth(s, s.layers[sh.first_layer + i].shader, depth + 1));
+		return 1 + d;
+	}
+
+	bool build(const FrayGpuScene& s, std::string& err)
+	{
+		blob.clear();
+		memset(&offsets, 0, sizeof(offsets));
+		features = 0;
+		if (s.abi_version != FRAY_GPU_ABI_VERSION) { err = "FrayGpuScene.abi_version mismatch"; return false; }
+		if (s.num_nodes < 0 || s.num_lights < 0 || s.settings.frame_width <= 0 || s.settings.frame_height <= 0) { err = "malformed scene header"; return false; }
+		auto inRange = [](long long i, long long n) { return i >= 0 && i < n; };
+
+		DScene<R>& d = offsets;
+		// camera + settings
+		cvt3(d.cam.pos, s.camera.pos);
+		cvt3(d.cam.topLeft, s.camera.top_left);
+		cvt3(d.cam.topRight, s.camera.top_right);
+		cvt3(d.cam.bottomLeft, s.camera.bottom_left);
+		cvt3(d.cam.front, s.camera.front);
+		cvt3(d.cam.up, s.camera.up);
+		cvt3(d.cam.right, s.camera.right);
+		d.cam.w = (R) s.camera.w;
+		d.cam.h = (R) s.camera.h;
+		d.cam.aperture = (R) s.camera.aperture_size;
+		d.cam.focalDist = (R) s.camera.focal_plane_dist;
+		d.cam.stereoSep = (R) s.camera.stereo_separation;
+		for (int i = 0; i < 3; i++) {
+			d.cam.leftMask[i] = s.camera.left_mask[i];
+			d.cam.rightMask[i] = s.camera.right_mask[i];
+			d.ambient[i] = s.settings.ambient[i];
+		}
+		d.cam.dof = s.camera.dof;
+		d.maxTraceDepth = s.settings.max_trace_depth;
+		d.gi = s.settings.gi;
+		d.saturation = s.settings.saturation;
+		d.numNodes = s.num_nodes;
+		d.numLights = s.num_lights;
+		d.hasEnv = s.has_environment;
+		for (int i = 0; i < 6; i++) {
+			d.env[i] = s.env_bitmaps[i];
+			if (d.env[i] >= s.num_bitmaps) { err = "environment bitmap index out of range"; return false; }
+		}
+
+		std::vector<DGeom<R>> geoms(s.num_geometries);
+		for (int i = 0; i < s.num_geometries; i++) {
+			const FrayGpuGeometry& g = s.geometries[i];
+			DGeom<R>& o = geoms[i];
+			o.type = g.type; o.mesh = g.mesh; o.left = g.left; o.right = g.right;
+			for (int k = 0; k < 4; k++) o.p[k] = (R) g.p[k];
+			if (g.type == FRAY_GEOM_MESH && !inRange(g.mesh, s.num_meshes)) { err = "geometry.mesh out of range"; return false; }
+			if (g.type >= FRAY_GEOM_CSG_PLUS && g.type <= FRAY_GEOM_CSG_MINUS) {
+				if (!inRange(g.left, s.num_geometries) || !inRange(g.right, s.num_geometries)) { err = "CSG operand out of range"; return false; }
+				features |= FRAY_F_CSG;
+			} else if (g.type < 0 || g.type > FRAY_GEOM_MESH) { err = "unknown geometry type"; return false; }
+		}
+
+		std::vector<DMesh<R>> meshes(s.num_meshes);
+		std::vector<DKdNode<R>> kd((size_t) s.num_kd_nodes);
+		std::vector<R> kdBox((size_t) s.num_kd_nodes * 6);
+		std::vector<int> leafRefs(s.leaf_refs, s.leaf_refs + s.num_leaf_refs);
+		const size_t T = (size_t) s.num_triangles;
+		std::vector<R> triA(3 * T), triAB(3 * T), triAC(3 * T), triN(3 * T), triG(3 * T), triDx(3 * T), triDy(3 * T);
+		std::vector<int> triNi(s.tri_n, s.tri_n + 3 * T), triTi(s.tri_t, s.tri_t + 3 * T);
+		for (size_t i = 0; i < 3 * T; i++) {
+			triAB[i] = (R) s.tri_ab[i]; triAC[i] = (R) s.tri_ac[i]; triN[i] = (R) s.tri_abxac[i]; triG[i] = (R) s.tri_gnormal[i];
+			triDx[i] = (R) s.tri_dndx[i]; triDy[i] = (R) s.tri_dndy[i];
+		}
+		for (int mi = 0; mi < s.num_meshes; mi++) {
+			const FrayGpuMesh& m = s.meshes[mi];
+			DMesh<R>& o = meshes[mi];
+			if (m.first_triangle < 0 || (long long) m.first_triangle + m.num_triangles > s.num_triangles ||
+			    m.first_vertex < 0 || (long long) m.first_vertex + m.num_vertices > s.num_vertices ||
+			    m.first_kd_node < 0 || (long long) m.first_kd_node + m.num_kd_nodes > s.num_kd_nodes ||
+			    m.first_leaf_ref < 0 || (long long) m.first_leaf_ref + m.num_leaf_refs > s.num_leaf_refs) { err = "mesh ranges out of bounds"; return false; }
+			o.flags = m.flags;
+			o.firstTri = m.first_triangle; o.numTris = m.num_triangles;
+			o.firstNormal = m.first_normal; o.firstUV = m.first_uv;
+			o.kdRoot = m.kd_root >= 0 ? m.first_kd_node + m.kd_root : -1;
+			o.firstLeafRef = m.first_leaf_ref;
+			o.pad = 0;
+			cvt3(o.bmin, m.bbox_min);
+			cvt3(o.bmax, m.bbox_max);
+			for (int t = 0; t < m.num_triangles; t++) {
+				const size_t ti = (size_t) m.first_triangle + t;
+				for (int k = 0; k < 3; k++) {
+					if (!inRange(s.tri_v[3 * ti + k], m.num_vertices)) { err = "triangle vertex index out of range"; return false; }
+					if ((m.flags & FRAY_MESH_HAS_NORMALS) && !inRange(s.tri_n[3 * ti + k], m.num_normals)) { err = "triangle normal index out of range"; return false; }
+					if ((m.flags & FRAY_MESH_HAS_UVS) && !inRange(s.tri_t[3 * ti + k], m.num_uvs)) { err = "triangle uv index out of range"; return false; }
+				}
+				cvt3(&triA[3 * ti], s.vertices + 3 * ((size_t) m.first_vertex + s.tri_v[3 * ti]));
+			}
+			// kd nodes: absolute indices + per-node boxes (in double, then rounded: the same values the reference's split() yields)
+			if (m.kd_root >= 0) {
+				struct Item { int node; double box[6]; };
+				std::vector<Item> todo;
+				Item root;
+				root.node = m.kd_root;
+				for (int k = 0; k < 3; k++) { root.box[k] = m.bbox_min[k]; root.box[3 + k] = m.bbox_max[k]; }
+				todo.push_back(root);
+				size_t visited = 0;
+				while (!todo.empty()) {
+					Item it = todo.back();
+					todo.pop_back();
+					if (!inRange(it.node, m.num_kd_nodes) || ++visited > (size_t) m.num_kd_nodes) { err = "malformed KD tree"; return false; }
+					const FrayGpuKdNode& n = s.kd_nodes[(size_t) m.first_kd_node + it.node];
+					DKdNode<R>& dn = kd[(size_t) m.first_kd_node + it.node];
+					for (int k = 0; k < 6; k++) kdBox[6 * ((size_t) m.first_kd_node + it.node) + k] = (R) it.box[k];
+					dn.axis = n.axis;
+					dn.split = (R) n.split;
+					if (n.axis == 3) {
+						if (n.a < 0 || n.b < 0 || n.a + n.b > m.num_leaf_refs) { err = "KD leaf range out of bounds"; return false; }
+						dn.a = m.first_leaf_ref + n.a;
+						dn.b = n.b;
+					} else {
+						if (n.axis < 0 || n.axis > 2 || !inRange(n.a, m.num_kd_nodes - 1)) { err = "malformed KD inner node"; return false; }
+						dn.a = m.first_kd_node + n.a;
+						dn.b = 0;
+						Item l = it, r = it;
+						l.node = n.a; r.node = n.a + 1;
+						l.box[3 + n.axis] = n.split;
+						r.box[n.axis] = n.split;
+						todo.push_back(l);
+						todo.push_back(r);
+					}
+				}
+				for (int i = 0; i < m.num_leaf_refs; i++)
+					if (!inRange(s.leaf_refs[(size_t) m.first_leaf_ref + i], m.num_triangles)) { err = "KD leaf reference out of range"; return false; }
+			}
+		}
+
+		std::vector<DShader<R>> shaders(s.num_shaders);
+		for (int i = 0; i < s.num_shaders; i++) {
+			const FrayGpuShader& sh = s.shaders[i];
+			DShader<R>& o = shaders[i];
+			o.type = sh.type; o.texture = sh.texture; o.firstLayer = sh.first_layer; o.numLayers = sh.num_layers;
+			o.numSamples = sh.num_samples; o.pureReflection = sh.pure_reflection;
+			for (int k = 0; k < 3; k++) { o.color[k] = sh.color[k]; o.specularColor[k] = sh.specular_color[k]; o.mult[k] = sh.mult[k]; }
+			o.exponent = (R) sh.exponent; o.specularMultiplier = (R) sh.specular_multiplier;
+			o.deflectionScaling = (R) sh.deflection_scaling; o.ior = (R) sh.ior;
+			if (sh.texture >= s.num_textures) { err = "shader texture out of range"; return false; }
+			if (sh.type == FRAY_SHADER_LAYERED) {
+				if (sh.first_layer < 0 || sh.num_layers < 0 || sh.first_layer + sh.num_layers > s.num_layers) { err = "layer range out of bounds"; return false; }
+				for (int k = 0; k < sh.num_layers; k++) {
+					const FrayGpuLayer& L = s.layers[sh.first_layer + k];
+					if (!inRange(L.shader, s.num_shaders) || L.texture >= s.num_textures) { err = "layer references out of range"; return false; }
+				}
+			}
+			if (sh.type == FRAY_SHADER_REFL && !sh.pure_reflection && sh.num_samples > FRAY_TASK_STACK - 16) {
+				err = "glossy numSamples exceeds the device ray-task stack";
+				return false;
+			}
+		}
+		for (int i = 0; i < s.num_shaders; i++)
+			if (layeredDepth(s, i, 0) > 2) { err = "Layered shaders nested deeper than 2 are not supported"; return false; }
+		std::vector<DLayer> layers(s.num_layers);
+		for (int i = 0; i < s.num_layers; i++) {
+			layers[i].shader = s.layers[i].shader;
+			layers[i].texture = s.layers[i].texture;
+			for (int k = 0; k < 3; k++) layers[i].opacity[k] = s.layers[i].opacity[k];
+		}
+		std::vector<DTexture<R>> textures(s.num_textures);
+		for (int i = 0; i < s.num_textures; i++) {
+			const FrayGpuTexture& t = s.textures[i];
+			DTexture<R>& o = textures[i];
+			o.type = t.type; o.bitmap = t.bitmap;
+			for (int k = 0; k < 3; k++) { o.color1[k] = t.color1[k]; o.color2[k] = t.color2[k]; }
+			o.scaling = (R) t.scaling; o.ior = (R) t.ior; o.bumpIntensity = (R) t.bump_intensity;
+			if ((t.type == FRAY_TEX_BITMAP || t.type == FRAY_TEX_BUMP) && !inRange(t.bitmap, s.num_bitmaps)) { err = "texture bitmap out of range"; return false; }
+		}
+		std::vector<DBitmap> bitmaps(s.num_bitmaps);
+		for (int i = 0; i < s.num_bitmaps; i++) {
+			const FrayGpuBitmap& b = s.bitmaps[i];
+			bitmaps[i].width = b.width; bitmaps[i].height = b.height; bitmaps[i].firstTexel = b.first_texel;
+			if (b.width <= 0 || b.height <= 0 || b.first_texel < 0 || b.first_texel + (long long) b.width * b.height > s.num_texels) { err = "bitmap texel range out of bounds"; return false; }
+		}
+		std::vector<DLight<R>> lights(s.num_lights);
+		for (int i = 0; i < s.num_lights; i++) {
+			const FrayGpuLight& l = s.lights[i];
+			DLight<R>& o = lights[i];
+			o.type = l.type; o.xSubd = l.x_subd; o.ySubd = l.y_subd;
+			for (int k = 0; k < 3; k++) o.color[k] = l.color[k];
+			o.power = l.power;
+			cvt3(o.pos, l.pos);
+			cvtXform(o.T, l.T);
+			cvt3(o.center, l.center);
+			o.area = (R) l.area;
+			o.areaF = (float) l.area;
+			if (l.type == FRAY_LIGHT_RECT && (l.x_subd < 1 || l.y_subd < 1)) { err = "RectLight subdivisions must be >= 1"; return false; }
+		}
+		std::vector<DNode<R>> nodes(s.num_nodes);
+		for (int i = 0; i < s.num_nodes; i++) {
+			const FrayGpuNode& n = s.nodes[i];
+			DNode<R>& o = nodes[i];
+			if (!inRange(n.geometry, s.num_geometries) || !inRange(n.shader, s.num_shaders) || n.bump >= s.num_textures) { err = "node references out of range"; return false; }
+			cvtXform(o.T, n.T);
+			o.geom = n.geometry; o.shader = n.shader; o.bump = n.bump;
+			o.needsUV = shaderReadsUV(s, n.shader, 0) || textureReadsUV(s, n.bump);
+		}
+		std::vector<R> normals(3 * (size_t) s.num_normals), uvs(3 * (size_t) s.num_uvs);
+		for (size_t i = 0; i < normals.size(); i++) normals[i] = (R) s.normals[i];
+		for (size_t i = 0; i < uvs.size(); i++) uvs[i] = (R) s.uvs[i];
+		std::vector<float> texels(s.texels, s.texels + 3 * (size_t) s.num_texels);
+
+#define FRAY_PUT(member, vec) d.member = reinterpret_cast<decltype(d.member)>(append(vec))
+		FRAY_PUT(nodes, nodes);
+		FRAY_PUT(geoms, geoms);
+		FRAY_PUT(meshes, meshes);
+		FRAY_PUT(shaders, shaders);
+		FRAY_PUT(layers, layers);
+		FRAY_PUT(textures, textures);
+		FRAY_PUT(bitmaps, bitmaps);
+		FRAY_PUT(lights, lights);
+		FRAY_PUT(triA, triA);
+		FRAY_PUT(triAB, triAB);
+		FRAY_PUT(triAC, triAC);
+		FRAY_PUT(triN, triN);
+		FRAY_PUT(triG, triG);
+		FRAY_PUT(triDndx, triDx);
+		FRAY_PUT(triDndy, triDy);
+		FRAY_PUT(triNi, triNi);
+		FRAY_PUT(triTi, triTi);
+		FRAY_PUT(normals, normals);
+		FRAY_PUT(uvs, uvs);
+		FRAY_PUT(kd, kd);
+		FRAY_PUT(kdBox, kdBox);
+		FRAY_PUT(leafRefs, leafRefs);
+		FRAY_PUT(texels, texels);
+#undef FRAY_PUT
+		return true;
+	}
+
+	// the scene with pointers rebased onto `base` (host: blob.data(); device: the cudaMalloc'ed copy)
+	DScene<R> bind(const void* base) const
+	{
+		DScene<R> d = offsets;
+		const char* b = (const char*) base;
+#define FRAY_REBASE(member) d.member = reinterpret_cast<decltype(d.member)>(b + (size_t) offsets.member)
+		FRAY_REBASE(nodes); FRAY_REBASE(geoms); FRAY_REBASE(meshes); FRAY_REBASE(shaders); FRAY_REBASE(layers);
+		FRAY_REBASE(textures); FRAY_REBASE(bitmaps); FRAY_REBASE(lights);
+		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
+		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
+		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
+#undef FRAY_REBASE
+		return d;
+	}
+};
+
+// samples per pixel by the reference's rule, src/main.cpp:395-400
+inline int samplesPerPixel(const FrayGpuScene& s)
+{
+	int spp = s.settings.want_aa ? 5 : 1;
+	if (s.camera.dof) spp = std::max(spp, s.camera.num_dof_samples);
+	if (s.settings.gi) spp = std::max(spp, s.settings.num_paths);
+	return spp;
+}
+
+} // namespace fray

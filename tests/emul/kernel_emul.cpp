@@ -1,0 +1,88 @@
+// kernel_emul.cpp -- TEST-ONLY host compilation of the per-ray device code (fray_b200/csrc/core.cuh).
+//
+// This container has no GPU. To debug the device algorithms (iterative path tracer, Whitted task stack, stack-based KD
+// descent, CSG lists, FP32 epsilon policy) before spending GPU minutes, the templated __host__ __device__ core is also
+// compiled here with g++ and driven by a plain loop over pixels and samples. It is NOT part of the product:
+// libfray_gpu.so neither links nor loads this file, the C ABI (include/fray_gpu.h) has no path to it, and the
+// `-m gpu` tests, smoke() and bench.py never use it. tests/test_emul_vs_oracle.py uses it as an early warning only.
+#include <atomic>
+#include <thread>
+#include <vector>
+#include <string>
+
+#include "../../fray_b200/csrc/scene_image.h"
+
+using namespace fray;
+
+template <typename R, int F>
+static void renderRows(const DScene<R>& sc, const FrayGpuFrame& fr, int W, int H, int spp, int s0, int s1, float* out,
+                       std::atomic<int>& nextRow, RayCounters& total)
+{
+	WhittedState<R>* ws = new WhittedState<R>;
+	ws->overflow = 0;
+	RayCounters cnt = { 0, 0, 0 };
+	const int bcount = fr.bucket_count > 0 ? fr.bucket_count : 1, brank = fr.bucket_count > 0 ? fr.bucket_rank : 0;
+	for (;;) {
+		int y = nextRow++;
+		if (y >= H) break;
+		for (int x = 0; x < W; x++) {
+			float* o = out + 3 * ((size_t) y * W + x);
+			const int BW = (W - 1) / 48 + 1, bx = x / 48, by = y / 48;
+			const int bucket = by * BW + ((by % 2 == 0) ? bx : (BW - 1 - bx));
+			if (bucket % bcount != brank) { o[0] = o[1] = o[2] = 0; continue; }
+			if (fr.mode == FRAY_RENDER_AOV) {
+				Ray<R> ray = screenRay(sc.cam, (R) x, (R) y, 0);
+				int node, light;
+				Hit<R> h;
+				closestHit<R, F>(sc, ray, node, light, h);
+				o[0] = light >= 0 ? (float) (-2 - light) : (float) node;
+				o[1] = (light < 0 && node >= 0 && h.tri >= 0) ? (float) (h.tri - sc.meshes[h.mesh].firstTri) : -1.0f;
+				o[2] = (float) h.dist;
+				continue;
+			}
+			Col sum(0, 0, 0);
+			for (int i = s0; i < s1; i++) sum = sum + renderSample<R, F>(sc, fr.seed, x, y, W, i, ws, cnt);
+			if (!(fr.flags & FRAY_FRAME_SUM)) sum = sum / (float) spp;
+			o[0] = sum.r; o[1] = sum.g; o[2] = sum.b;
+		}
+	}
+	static std::atomic_flag lock = ATOMIC_FLAG_INIT;
+	while (lock.test_and_set()) {}
+	total.rays += cnt.rays; total.primary += cnt.primary; total.shadow += cnt.shadow;
+	lock.clear();
+	delete ws;
+}
+
+template <typename R>
+static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out, FrayGpuStats* stats, int threads)
+{
+	SceneImage<R> img;
+	std::string err;
+	if (!img.build(*scene, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+	DScene<R> sc = img.bind(img.blob.data());
+	const int W = scene->settings.frame_width, H = scene->settings.frame_height;
+	const int spp = fr->spp > 0 ? fr->spp : samplesPerPixel(*scene);
+	int s0 = fr->sample_begin, s1 = fr->sample_end;
+	if (s0 == 0 && s1 == 0) s1 = spp;
+	if (threads < 1) threads = (int) std::thread::hardware_concurrency();
+	std::atomic<int> nextRow(0);
+	RayCounters total = { 0, 0, 0 };
+	std::vector<std::thread> pool;
+	auto run = [&]() {
+		if (img.features & FRAY_F_CSG) renderRows<R, FRAY_F_CSG>(sc, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else renderRows<R, 0>(sc, *fr, W, H, spp, s0, s1, out, nextRow, total);
+	};
+	for (int t = 1; t < threads; t++) pool.emplace_back(run);
+	run();
+	for (auto& t: pool) t.join();
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		stats->rays = total.rays; stats->primary_rays = total.primary; stats->shadow_rays = total.shadow;
+	}
+	return 0;
+}
+
+extern "C" int fray_emul_render(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out, FrayGpuStats* stats, int precision, int threads)
+{
+	return precision == FRAY_GPU_FP64 ? renderT<double>(scene, fr, out, stats, threads) : renderT<float>(scene, fr, out, stats, threads);
+}
