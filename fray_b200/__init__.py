@@ -105,6 +105,9 @@ def host_lib() -> C.CDLL:
         L.fray_host_save_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         L.fray_host_load_image.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.fray_host_free_pixels.argtypes = [C.POINTER(C.c_float)]
+        L.fray_host_rng_draws.argtypes = [C.c_uint32] * 4 + [C.c_int, C.c_void_p]
+        L.fray_host_rng_child.restype = C.c_uint32
+        L.fray_host_rng_child.argtypes = [C.c_uint32] * 3
         _host = L
     return _host
 
@@ -128,6 +131,7 @@ def gpu_lib() -> C.CDLL:
         L.fray_gpu_resolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.fray_gpu_sync.argtypes = [C.c_void_p, C.POINTER(FrayStats)]
         L.fray_gpu_destroy.argtypes = [C.c_void_p]
+        L.fray_gpu_measure_peaks.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _gpu = L
     return _gpu
 
@@ -248,6 +252,16 @@ class GpuContext:
         stats = FrayStats()
         self._check(self._lib.fray_gpu_sync(self._ctx, C.byref(stats)), "fray_gpu_sync")
         return RenderStats.of(stats)
+
+
+def measure_peaks(device: int = 0, ms: float = 20.0) -> tuple[float, float]:
+    """(sustained FP32 FFMA TFLOP/s, L2-resident read GB/s) measured on `device` right now."""
+    L = gpu_lib()
+    f, l2 = C.c_double(), C.c_double()
+    rc = L.fray_gpu_measure_peaks(device, ms, C.byref(f), C.byref(l2))
+    if rc != 0:
+        raise FrayError(f"fray_gpu_measure_peaks failed ({rc}): {L.fray_gpu_last_error().decode(errors='replace')}")
+    return f.value, l2.value
 
 
 def save_image(path: str, rgb: np.ndarray):

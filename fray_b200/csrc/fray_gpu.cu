@@ -6,6 +6,7 @@
 // There is no CPU code path: if CUDA is unavailable every entry point fails with FRAY_GPU_ENODEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -46,6 +47,7 @@ struct FrayGpuCtx {
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
 	int4* dBuckets = nullptr;
 	int bucketCapacity = 0;
+	int cachedBucketCount = -1, cachedBucketRank = -1, cachedOwned = 0; // what dBuckets currently holds
 	unsigned long long* dCounters = nullptr; // 3 counters
 	unsigned int* dWork = nullptr;
 	int* dError = nullptr;
@@ -61,6 +63,32 @@ struct FrayGpuCtx {
 __global__ void resolveKernel(const float* __restrict__ sum, float* __restrict__ rgb, size_t n, float spp)
 {
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) rgb[i] = sum[i] / spp;
+}
+
+// ---- roofline denominators ---------------------------------------------------------------------------
+__global__ void ffmaPeakKernel(float* sink, int iters, float a, float b)
+{
+	float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+			x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+		}
+	}
+	const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+	if (r == 123.456f) sink[0] = r; // never true: keeps the chains alive
+}
+
+__global__ void l2ReadKernel(const float4* __restrict__ buf, size_t n, int passes, float* sink)
+{
+	float acc = 0;
+	for (int p = 0; p < passes; p++)
+		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+			const float4 v = __ldcg(buf + i); // cache at L2 only
+			acc += v.x + v.y + v.z + v.w;
+		}
+	if (acc == 123.456f) sink[0] = acc;
 }
 
 template <typename R> static void convertCamera(DCamera<R>& d, const FrayGpuCamera& cam)
@@ -232,6 +260,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 		c->bucketCapacity = 0;
 		CUDA_TRY(cudaMalloc(&c->dBuckets, all.size() * sizeof(int4)));
 		c->bucketCapacity = (int) all.size();
+		c->cachedBucketCount = -1;
 	}
 
 	RenderParams p;
@@ -252,7 +281,13 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	p.errorFlag = c->dError;
 
 	if (owned.size() != all.size()) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
-	if (!owned.empty()) CUDA_TRY(cudaMemcpyAsync(c->dBuckets, owned.data(), owned.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+	if (!owned.empty() && (c->cachedBucketCount != bcount || c->cachedBucketRank != brank || c->cachedOwned != (int) owned.size())) {
+		CUDA_TRY(cudaMemcpyAsync(c->dBuckets, owned.data(), owned.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream)); // `owned` is a pageable temporary
+		c->cachedBucketCount = bcount;
+		c->cachedBucketRank = brank;
+		c->cachedOwned = (int) owned.size();
+	}
 	CUDA_TRY(cudaMemsetAsync(c->dCounters, 0, 3 * sizeof(unsigned long long), stream));
 	CUDA_TRY(cudaMemsetAsync(c->dWork, 0, sizeof(unsigned int), stream));
 
@@ -341,6 +376,60 @@ int fray_gpu_resolve_device(FrayGpuCtx* c, const void* d_sum, void* d_rgb, int32
 	const size_t n = (size_t) c->width * c->height * 3;
 	cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : c->stream;
 	resolveKernel<<<c->numSMs * 4, 256, 0, st>>>((const float*) d_sum, (float*) d_rgb, n, (float) spp);
+	CUDA_TRY(cudaGetLastError());
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_measure_peaks(int device, double ms, double* fp32_tflops, double* l2_gbs)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(FRAY_GPU_ENODEVICE, "no CUDA device available");
+	}
+	if (device < 0 || device >= ndev) return fail(FRAY_GPU_EINVAL, "device ordinal out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));
+	CUDA_TRY(cudaEventCreate(&e1));
+	float* sink = nullptr;
+	CUDA_TRY(cudaMalloc(&sink, 256));
+	float t = 0;
+	if (fp32_tflops) {
+		const int blocks = prop.multiProcessorCount * 8, threads = 256;
+		int iters = 2000;
+		for (int round = 0; round < 3; round++) { // calibrate to ~ms
+			CUDA_TRY(cudaEventRecord(e0));
+			ffmaPeakKernel<<<blocks, threads>>>(sink, iters, 1.0000001f, 1e-9f);
+			CUDA_TRY(cudaEventRecord(e1));
+			CUDA_TRY(cudaEventSynchronize(e1));
+			CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+			if (round < 2 && t > 0) iters = (int) std::min(2e6, std::max(100.0, iters * ms / t));
+		}
+		*fp32_tflops = 2.0 * 8 * 16 * (double) iters * blocks * threads / (t * 1e-3) / 1e12;
+	}
+	if (l2_gbs) {
+		const size_t bytes = 32u << 20, n = bytes / sizeof(float4);
+		float4* buf = nullptr;
+		CUDA_TRY(cudaMalloc(&buf, bytes));
+		CUDA_TRY(cudaMemset(buf, 0, bytes));
+		int passes = 20;
+		for (int round = 0; round < 3; round++) {
+			CUDA_TRY(cudaEventRecord(e0));
+			l2ReadKernel<<<prop.multiProcessorCount * 8, 256>>>(buf, n, passes, sink);
+			CUDA_TRY(cudaEventRecord(e1));
+			CUDA_TRY(cudaEventSynchronize(e1));
+			CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+			if (round < 2 && t > 0) passes = (int) std::min(5000.0, std::max(4.0, passes * ms / t));
+		}
+		*l2_gbs = (double) bytes * passes / (t * 1e-3) / 1e9;
+		cudaFree(buf);
+	}
+	cudaFree(sink);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
 	CUDA_TRY(cudaGetLastError());
 	return FRAY_GPU_OK;
 }

@@ -1,0 +1,99 @@
+"""Multi-GPU rendering: one process per GPU (torchrun), `torch.distributed` over NCCL for the one exchange step.
+
+The reference distributes 48x48 buckets to threads through an atomic cursor (/root/reference/src/main.cpp:323-371,
+src/sdl.cpp:243-262) and every thread writes its own pixels of the shared `vfb`. Across GPUs the same decomposition is
+static and needs exactly one collective at the end of the frame:
+
+* ``tiles``   -- rank r owns the buckets b of the serpentine list with b % world == r, renders all samples of them and
+                 leaves zeros elsewhere; the partial frames are summed onto rank 0 (``reduce(SUM)``; disjoint pixels, so
+                 the sum is exact) and divided by spp there.
+* ``samples`` -- rank r renders samples [r*spp/world, (r+1)*spp/world) of EVERY pixel (possible because the counter-based
+                 RNG makes sample i of pixel p independent of who renders it); ``reduce(SUM)`` then / spp. Best load
+                 balance; the result equals the single-GPU frame up to FP32 summation order.
+
+The scene is replicated (the largest bundled scene is ~25 MB). There is no collective inside the render path.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+import fray_b200 as fb
+
+
+def shard(rank: int, world: int, spp: int, mode: str) -> dict:
+    """Frame keyword arguments (see FrayGpuFrame) that select rank `rank`'s share of the frame."""
+    if world <= 1:
+        return {}
+    if mode == "tiles":
+        return dict(bucket_rank=rank, bucket_count=world)
+    if mode == "samples":
+        if spp < world:
+            raise ValueError(f"cannot split {spp} samples over {world} ranks; use mode='tiles'")
+        return dict(sample_begin=(rank * spp) // world, sample_end=((rank + 1) * spp) // world)
+    raise ValueError(f"unknown shard mode {mode!r}")
+
+
+def choose_mode(spp: int, world: int) -> str:
+    return "samples" if spp >= 8 * world else "tiles"
+
+
+def reduce_partials(partial, spp: int, group=None):
+    """Sum per-rank partial SUM frames (torch tensors, any device) onto rank 0 and resolve: returns sum / spp on rank 0,
+    None elsewhere. With an un-initialised process group this is the single-process identity."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM, group=group)
+        if dist.get_rank(group) != 0:
+            return None
+    return partial / float(spp)
+
+
+class DistributedRenderer:
+    """One rank of a multi-GPU render. Rank 0 ends up with the finished frame."""
+
+    def __init__(self, scene: fb.Scene, mode: str = "auto", precision: int = fb.FP32, device: int | None = None):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.dist = dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+        torch.cuda.set_device(self.device)
+        self.scene = scene
+        self.spp = scene.spp
+        self.mode = choose_mode(self.spp, self.world) if mode == "auto" else mode
+        self.ctx = fb.GpuContext(scene, self.device, precision)
+        h, w = scene.height, scene.width
+        self.partial = torch.zeros((h, w, 3), dtype=torch.float32, device=f"cuda:{self.device}")
+        self.frame = torch.zeros_like(self.partial) if self.rank == 0 else None
+        self.host_frame = torch.empty((h, w, 3), dtype=torch.float32).pin_memory() if self.rank == 0 else None
+
+    def render_device(self, seed: int = 42):
+        """Kernels + the NCCL reduce, everything enqueued on torch's current stream. Rank 0: self.frame holds the image."""
+        torch = self.torch
+        stream = torch.cuda.current_stream().cuda_stream
+        kw = shard(self.rank, self.world, self.spp, self.mode)
+        self.ctx.render_device(self.partial.data_ptr(), stream, spp=self.spp, seed=seed, flags=fb.FRAME_SUM, **kw)
+        if self.world > 1:
+            self.dist.reduce(self.partial, dst=0, op=self.dist.ReduceOp.SUM)
+        if self.rank == 0:
+            self.ctx.resolve_device(self.partial.data_ptr(), self.frame.data_ptr(), self.spp, stream)
+
+    def render(self, seed: int = 42) -> np.ndarray | None:
+        """End to end: render, reduce, and bring the frame to (pinned) host memory on rank 0."""
+        self.render_device(seed)
+        if self.rank != 0:
+            return None
+        self.host_frame.copy_(self.frame, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self.host_frame.numpy()
+
+    def stats(self) -> fb.RenderStats:
+        return self.ctx.sync()
+
+    def close(self):
+        self.ctx.close()

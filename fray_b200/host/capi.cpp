@@ -4,6 +4,7 @@
 
 #include "scene.h"
 #include "fray_host.h"
+#include "../csrc/rng.cuh"
 
 using namespace fray;
 
@@ -17,6 +18,8 @@ static thread_local std::string g_error;
 extern "C" {
 
 const char* fray_host_last_error(void) { return g_error.c_str(); }
+
+void fray_host_set_verbose(int verbose) { g_verbose = verbose; }
 
 FrayHostScene* fray_host_load_scene(const char* path)
 {
@@ -129,5 +132,14 @@ int fray_host_load_image(const char* path, float** rgb, int* width, int* height)
 }
 
 void fray_host_free_pixels(float* rgb) { free(rgb); }
+
+void fray_host_rng_draws(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t branch, int n, uint32_t* out)
+{
+	Rng r;
+	r.init(seed, pixel, sample, branch);
+	for (int i = 0; i < n; i++) out[i] = r.next();
+}
+
+uint32_t fray_host_rng_child(uint32_t branch, uint32_t draws, uint32_t k) { return rngChildBranch(branch, draws, k); }
 
 } // extern "C"

@@ -242,7 +242,7 @@ void Mesh::prepareTriangles()
 			t.dNdy = Vec3();
 		}
 	}
-	printf("Mesh loaded, %d triangles\n", (int) triangles.size());
+	if (g_verbose) printf("Mesh loaded, %d triangles\n", (int) triangles.size());
 }
 
 // ---- KD build --------------------------------------------------------------------------------------
@@ -303,7 +303,7 @@ void Mesh::beginRender()
 		kdNodes.push_back(FrayGpuKdNode{});
 		buildKD(0, all, bbox, 0);
 		unsigned ms = (unsigned) std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
-		printf("KD Tree for %d triangles built in %u milliseconds (%d nodes, max depth = %d, avg depth = %.1f)\n",
+		if (g_verbose) printf("KD Tree for %d triangles built in %u milliseconds (%d nodes, max depth = %d, avg depth = %.1f)\n",
 		       (int) triangles.size(), ms, numNodes, maxTreeDepth, nodeDepthSum / float(numNodes));
 	}
 	if (normals.empty()) faceted = true;

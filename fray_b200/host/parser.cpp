@@ -18,6 +18,8 @@
 
 namespace fray {
 
+int g_verbose = 0;
+
 static bool fileExists(const std::string& fn) // src/util.cpp:57-66
 {
 	std::string t = fn;
@@ -445,7 +447,7 @@ bool Parser::parse(const char* filename, Scene* scene)
 				if (pb->element->getElementType() != et) continue;
 				pb->element->fillProperties(*pb);
 				for (auto& l: pb->lines)
-					if (!l.recognized)
+					if (!l.recognized && g_verbose)
 						fprintf(stderr, "%s:%d: Warning: the property `%s' isn't recognized!\n", filename, l.line, l.name.c_str());
 			}
 	} catch (const SyntaxError& err) {

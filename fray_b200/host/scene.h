@@ -18,6 +18,10 @@
 
 namespace fray {
 
+// progress / statistics lines the reference prints to stdout ("Mesh loaded", "KD Tree ... built"); the command line tool
+// turns them on, library users get a quiet stdout
+extern int g_verbose;
+
 enum ElementType { // src/scene.h:30-39
 	ELEM_GEOMETRY, ELEM_SHADER, ELEM_NODE, ELEM_TEXTURE, ELEM_ENVIRONMENT, ELEM_CAMERA, ELEM_SETTINGS, ELEM_LIGHT,
 };

@@ -309,6 +309,11 @@ int fray_gpu_sync(FrayGpuCtx* ctx, FrayGpuStats* stats);
 
 void fray_gpu_destroy(FrayGpuCtx* ctx);
 
+/* Roofline denominators measured on the spot (bench.py): sustained FP32 FFMA rate of `device` in TFLOP/s (8 independent
+ * FMA chains per thread, all SMs, ~`ms` milliseconds) and L2-resident read bandwidth in GB/s (a 32 MiB buffer read
+ * repeatedly with 128-bit loads). Either output may be NULL. */
+int fray_gpu_measure_peaks(int device, double ms, double* fp32_tflops, double* l2_gbs);
+
 const char* fray_gpu_last_error(void);
 
 #ifdef __cplusplus

@@ -23,6 +23,9 @@ FrayHostScene* fray_host_load_scene(const char* path);
 void fray_host_free_scene(FrayHostScene* scene);
 const char* fray_host_last_error(void);
 
+/* 1: print the reference's progress lines ("Mesh loaded, N triangles", KD statistics, unknown-property warnings); default 0 */
+void fray_host_set_verbose(int verbose);
+
 /* The flattened scene; valid until the next fray_host_* call that mutates the scene, or free. */
 const FrayGpuScene* fray_host_flat_scene(const FrayHostScene* scene);
 
@@ -46,6 +49,12 @@ int fray_host_save_image(const char* path, const float* rgb, int width, int heig
 /* Load .bmp / .exr into a malloc'ed float[h][w][3]; caller frees with fray_host_free_pixels(). */
 int fray_host_load_image(const char* path, float** rgb, int* width, int* height);
 void fray_host_free_pixels(float* rgb);
+
+/* The product's counter-based RNG (fray_b200/csrc/rng.cuh, the code the kernels run) evaluated on the host: the first
+ * `n` 32-bit draws of stream (seed, pixel, sample, branch), and the branch id of a Whitted secondary ray.
+ * Exposed so that tests can hold it against the contract stated in DESIGN.md draw for draw. */
+void fray_host_rng_draws(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t branch, int n, uint32_t* out);
+uint32_t fray_host_rng_child(uint32_t branch, uint32_t draws, uint32_t k);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,7 @@ def oracle_lib() -> C.CDLL:
         L.fray_oracle_screen_ray.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         L.fray_oracle_intersect.argtypes = [C.c_void_p] * 4
         L.fray_oracle_environment.argtypes = [C.c_void_p] * 3
+        L.fray_oracle_work_profile.argtypes = [C.c_void_p]
         _oracle = L
     return _oracle
 
@@ -57,6 +58,30 @@ def oracle_render(scene: fb.Scene, threads: int = 0, **frame_kw):
     if rc != 0:
         raise RuntimeError("fray_oracle_render failed")
     return out, fb.RenderStats.of(stats)
+
+
+PROFILE_KEYS = ["node_tests", "node_hits", "root_box_tests", "kd_inner", "kd_leaf", "tri_calls", "tri_tests", "plane_tests", "sphere_tests",
+                "cube_tests", "light_tests", "light_samples", "hemi_samples", "brdf_evals", "texture_lookups", "leaf_refs"]
+
+# algorithmic cost model of SURVEY.md section 8(d): FP32 flops (FMA = 2) and bytes per occurrence
+FLOP_COST = dict(node_tests=43, node_hits=52, root_box_tests=20, kd_inner=4, kd_leaf=0, tri_calls=6, tri_tests=40, plane_tests=22, sphere_tests=40,
+                 cube_tests=60, light_tests=55, light_samples=45, hemi_samples=60, brdf_evals=12, texture_lookups=15, leaf_refs=0)
+BYTE_COST = dict(node_tests=96, node_hits=0, root_box_tests=24, kd_inner=16, kd_leaf=16, tri_calls=16, tri_tests=48, plane_tests=8, sphere_tests=16,
+                 cube_tests=16, light_tests=96, light_samples=32, hemi_samples=0, brdf_evals=32, texture_lookups=12, leaf_refs=4)
+
+
+def oracle_work_profile() -> dict:
+    """Counters of the last oracle_render call (how often each piece of the hot path ran)."""
+    buf = (C.c_uint64 * 16)()
+    oracle_lib().fray_oracle_work_profile(buf)
+    return dict(zip(PROFILE_KEYS, (int(v) for v in buf)))
+
+
+def algorithmic_work_per_ray(profile: dict, rays: int) -> tuple[float, float]:
+    """(flop per ray, bytes per ray) under the cost model above."""
+    flop = sum(profile[k] * FLOP_COST[k] for k in PROFILE_KEYS) / rays
+    byts = sum(profile[k] * BYTE_COST[k] for k in PROFILE_KEYS) / rays
+    return flop, byts
 
 
 def read_dump(path: str) -> np.ndarray:

@@ -1,0 +1,55 @@
+"""Early-warning check that needs no GPU: the per-ray device code (fray_b200/csrc/core.cuh), compiled for the host by
+tests/emul/kernel_emul.cpp, against the oracle. The real parity tests are the `-m gpu` ones (test_gpu_parity.py), which go
+through the C ABI of libfray_gpu.so; this file only guards the shared templated core while developing without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fray_b200 as fb
+import oracle_util as ou
+from conftest import golden_scene, load_golden
+
+EMUL_DIR = os.path.join(fb.REPO_ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL_DIR, "libfray_emul.so")
+    src = os.path.join(EMUL_DIR, "kernel_emul.cpp")
+    deps = [src] + [os.path.join(fb.REPO_ROOT, "fray_b200", "csrc", f) for f in ("core.cuh", "rng.cuh", "scene_image.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-x", "c++", src,
+                               "-o", so, "-lpthread"])
+    lib = C.CDLL(so)
+    lib.fray_emul_render.argtypes = [C.c_void_p, C.POINTER(fb.FrayFrame), C.c_void_p, C.POINTER(fb.FrayStats), C.c_int, C.c_int]
+
+    def render(scene, precision, **kw):
+        out = np.empty((scene.height, scene.width, 3), np.float32)
+        frame, stats = fb.make_frame(**kw), fb.FrayStats()
+        assert lib.fray_emul_render(scene.flat, C.byref(frame), out.ctypes.data, C.byref(stats), precision, 0) == 0
+        return out, fb.RenderStats.of(stats)
+    return render
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "smallpt", "boxed", "forest", "forest_stereo_dof", "bokeh", "dragon"])
+def test_device_core_fp64_matches_golden(name, emul, golden_cases, data_dir):
+    path, seed = golden_scene(golden_cases, name)
+    sc = fb.Scene(path)
+    want, ostats = ou.oracle_render(sc, seed=seed)
+    got, stats = emul(sc, fb.FP64, seed=seed)
+    frac, rmse, mx = ou.compare(want, got, 1e-5)
+    assert frac == 1.0 and mx < 2e-5, (frac, rmse, mx)
+    assert stats.rays == ostats.rays  # the same rays, one for one
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "smallpt", "boxed", "forest"])
+def test_device_core_fp32_within_tolerance(name, emul, golden_cases, data_dir):
+    path, seed = golden_scene(golden_cases, name)
+    sc = fb.Scene(path)
+    want, _, _ = load_golden(name)
+    got, _ = emul(sc, fb.FP32, seed=seed)
+    frac, rmse, mx = ou.compare(want, got, 1e-3)
+    assert frac >= 0.997, (frac, rmse, mx)
