@@ -21,6 +21,8 @@ import numpy as np
 
 import fray_b200 as fb
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the default stream as an explicit handle
+
 
 def shard(rank: int, world: int, spp: int, mode: str) -> dict:
     """Frame keyword arguments (see FrayGpuFrame) that select rank `rank`'s share of the frame."""
@@ -75,7 +77,8 @@ class DistributedRenderer:
     def render_device(self, seed: int = 42):
         """Kernels + the NCCL reduce, everything enqueued on torch's current stream. Rank 0: self.frame holds the image."""
         torch = self.torch
-        stream = torch.cuda.current_stream().cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "the context's own stream": name it explicitly
+        stream = torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
         kw = shard(self.rank, self.world, self.spp, self.mode)
         self.ctx.render_device(self.partial.data_ptr(), stream, spp=self.spp, seed=seed, flags=fb.FRAME_SUM, **kw)
         if self.world > 1:

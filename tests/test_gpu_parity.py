@@ -91,16 +91,23 @@ def test_fp32_pathtraced_same_seed_rmse(name, scenes):
     ctx.close()
 
 
-def test_fp32_dragon_and_bokeh_statistically(scenes):
-    """bokeh: a bitmap magnified 250x per unit cannot be texel-exact from FP32 hit points; dragon: glossy. Means agree."""
-    for name, tol in (("bokeh", 0.01), ("dragon", 0.02)):
-        sc, seed = scenes(name)
-        ref, _, _ = load_golden(name)
-        ctx = fb.GpuContext(sc, 0, fb.FP32)
-        got, _ = ctx.render(seed=seed)
-        assert abs(got.mean() - ref.mean()) <= tol * ref.mean(), name
-        assert ou.compare(ref, got, 0.05)[0] > 0.9, name
-        ctx.close()
+def test_fp32_dragon_and_bokeh(scenes):
+    """dragon (glossy floor: per-ray derived streams, so the pin is the oracle, not the sequential-stream golden) and
+    bokeh (a bitmap repeated 250x per unit cannot be texel-exact from FP32 hit points: means and a loose tolerance)."""
+    sc, seed = scenes("dragon")
+    want, _ = ou.oracle_render(sc, seed=seed)
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    got, _ = ctx.render(seed=seed)
+    frac, rmse, mx = ou.compare(want, got, 1e-3)
+    assert frac >= 0.995, (frac, rmse, mx)
+    ctx.close()
+    sc, seed = scenes("bokeh")
+    ref, _, _ = load_golden("bokeh")
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    got, _ = ctx.render(seed=seed)
+    assert abs(got.mean() - ref.mean()) <= 0.01 * ref.mean()
+    assert ou.compare(ref, got, 0.05)[0] > 0.9
+    ctx.close()
 
 
 @pytest.mark.parametrize("precision", [fb.FP32, fb.FP64])
@@ -139,7 +146,7 @@ def test_render_device_and_resolve(scenes):
     want, _ = ctx.render(seed=seed)
     part = torch.zeros((sc.height, sc.width, 3), dtype=torch.float32, device="cuda:0")
     out = torch.empty_like(part)
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream().cuda_stream or 1  # 1 = cudaStreamLegacy
     ctx.render_device(part.data_ptr(), stream, seed=seed, flags=fb.FRAME_SUM)
     ctx.resolve_device(part.data_ptr(), out.data_ptr(), sc.spp, stream)
     stats = ctx.sync()
