@@ -20,6 +20,7 @@
 #include <float.h>
 
 #include "rng.cuh"
+#include "flat.cuh"
 #include "../../include/fray_gpu.h"
 
 namespace fray {
@@ -141,6 +142,8 @@ template <typename R> struct DNode {
 	DXform<R> T;
 	int geom, shader, bump;
 	int needsUV; // some texture on this node reads (u, v); otherwise sphere uv (atan2/asin) is skipped in fast precision
+	int inFlat;  // fast precision: the node's triangles live in the flat polygon table (flat.cuh) and the node loop skips it
+	int pad[3];
 };
 
 template <typename R> struct DGeom {
@@ -233,6 +236,12 @@ template <typename R> struct DScene {
 	const R* kdBox;     // 6 R per kd node: vmin xyz, vmax xyz
 	const int* leafRefs; // triangle indices relative to mesh.firstTri
 	const float* texels;
+	// fast precision only (flat.cuh): world-space convex polygons of the brute-force meshes and the rectangular lights
+	const float4* flatPolys;   // FRAY_FLAT_POLY_VEC float4 per polygon
+	const FlatInfo* flatInfo;  // one per polygon
+	int numFlatGeom;           // polygons [0, numFlatGeom) are node geometry (occluders)
+	int numFlatAll;            // polygons [numFlatGeom, numFlatAll) are lights
+	int lightsInFlat;          // the rectangular lights are in the table: the light loop of closestHit is skipped
 };
 
 template <typename R> struct Ray {
@@ -642,8 +651,37 @@ template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
 	FRAY_HD static bool run(const DScene<R>&, int, const Ray<R>&, Hit<R>&) { return false; } // rejected at flatten time
 };
 
-// feature bits: code paths that cost local memory / registers are compiled in only for scenes that need them
-#define FRAY_F_CSG 1
+// feature bits (template parameter F of the kernels): code paths that cost registers, local memory and instruction-cache
+// footprint are compiled in only for scenes that need them. Parity precision always runs with FRAY_F_NODES | FRAY_F_TEX.
+#define FRAY_F_CSG 1    // CSG geometry exists
+#define FRAY_F_NODES 2  // some node is traced through the generic node loop (analytic primitives, KD meshes)
+#define FRAY_F_TEX 4    // textures, bump maps or an environment exist
+#define FRAY_F_FLAT 8   // fast precision: the flat polygon table (flat.cuh) holds the brute-force meshes and the lights
+#define FRAY_F_ATTR 16  // some flat record interpolates normals / uvs
+#define FRAY_F_GENERIC (FRAY_F_NODES | FRAY_F_TEX)
+
+// The kernel variants compiled per precision, smallest first; a scene runs on the first one that covers its feature bits.
+template <typename R> struct Variants;
+template <> struct Variants<float> {
+	static constexpr int count = 4;
+	static constexpr int mask(int i)
+	{
+		return i == 0 ? FRAY_F_FLAT                                              // brute-force meshes + lights only (cornell_box)
+		     : i == 1 ? (FRAY_F_FLAT | FRAY_F_NODES)                               // + analytic primitives / KD meshes, untextured (smallpt)
+		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX)    // everything but CSG
+		              : (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
+	}
+};
+template <> struct Variants<double> {
+	static constexpr int count = 2;
+	static constexpr int mask(int i) { return i == 0 ? FRAY_F_GENERIC : (FRAY_F_GENERIC | FRAY_F_CSG); }
+};
+
+// where the kernels staged the flat table (shared memory on the GPU, the scene blob in the host emulator)
+struct FlatTab {
+	const float4* polys;
+	const FlatInfo* info;
+};
 
 // Node::intersect, src/geometry.cpp:196-208. On success h is in WORLD space (ip, norm, dist).
 // `maxDist` bounds the search in world units: hits farther away may be dropped (closest-hit pruning against the best
@@ -684,7 +722,7 @@ FRAY_HD bool intersectNode(const DScene<R>& sc, int ni, const Ray<R>& ray, R max
 }
 
 // visible(), src/main.cpp:64-80
-template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const V3<R>& a, const V3<R>& b, RayCounters& cnt)
+template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const FlatTab& ft, const V3<R>& a, const V3<R>& b, RayCounters& cnt)
 {
 	cnt.rays++;
 	cnt.shadow++;
@@ -693,9 +731,15 @@ template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const
 	ray.start = a;
 	const R maxDist = length(ray.dir);
 	ray.dir = normalized(ray.dir);
-	for (int n = 0; n < sc.numNodes; n++) {
-		Hit<R> h;
-		if (intersectNode<R, true, F>(sc, n, ray, maxDist, h) && h.dist < maxDist) return false;
+	if constexpr ((F & FRAY_F_FLAT) != 0 && !Num<R>::kExact) {
+		if (flatAny(ft.polys, sc.numFlatGeom, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+	}
+	if (F & FRAY_F_NODES) {
+		for (int n = 0; n < sc.numNodes; n++) {
+			if ((F & FRAY_F_FLAT) && sc.nodes[n].inFlat) continue;
+			Hit<R> h;
+			if (intersectNode<R, true, F>(sc, n, ray, maxDist, h) && h.dist < maxDist) return false;
+		}
 	}
 	return true;
 }
@@ -715,26 +759,68 @@ template <typename R> FRAY_HD bool intersectLight(const DLight<R>& l, const Ray<
 	return true;
 }
 
+// barycentrics of world point `p` in triangle `tri` of node `nd` (flat records that interpolate attributes)
+template <typename R> FRAY_HD void flatBarycentrics(const DScene<R>& sc, const DNode<R>& nd, int tri, const V3<R>& p, R& l2, R& l3)
+{
+	const size_t o = 3 * (size_t) tri;
+	const V3<R> H = xfUnpoint(nd.T, p) - load3(sc.triA + o);
+	const V3<R> N = load3(sc.triN + o), AB = load3(sc.triAB + o), AC = load3(sc.triAC + o);
+	const R rNN = 1 / dot(N, N);
+	l2 = dot(cross(H, AC), N) * rNN;
+	l3 = dot(cross(AB, H), N) * rNN;
+}
+
 // the two closest-hit loops of raytrace()/pathtrace(), src/main.cpp:178-199, 250-271
-template <typename R, int F> FRAY_HD_HOT void closestHit(const DScene<R>& sc, const Ray<R>& ray, int& node, int& light, Hit<R>& best)
+template <typename R, int F>
+FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>& ray, int& node, int& light, Hit<R>& best)
 {
 	node = -1;
 	light = -1;
 	best.dist = Num<R>::big();
 	best.tri = -1;
 	best.mesh = -1;
-	for (int n = 0; n < sc.numNodes; n++) {
-		Hit<R> h;
-		if (intersectNode<R, false, F>(sc, n, ray, best.dist, h) && h.dist < best.dist) {
-			best = h;
-			node = n;
+	if constexpr ((F & FRAY_F_FLAT) != 0 && !Num<R>::kExact) {
+		int idx = -1;
+		flatClosest(ft.polys, sc.numFlatAll, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
+		if (idx >= 0) {
+			const FlatInfo& fi = ft.info[idx];
+			if (fi.flags & FRAY_FLAT_LIGHT) {
+				light = fi.node;
+			} else {
+				node = fi.node;
+				best.ip = ray.start + ray.dir * best.dist;
+				best.norm = V3<R>(fi.nx, fi.ny, fi.nz);
+				best.u = best.v = 0;
+				best.mesh = fi.mesh;
+				best.tri = fi.tri0;
+				if ((fi.flags & FRAY_FLAT_QUAD) && fi.diag.x * best.ip.x + fi.diag.y * best.ip.y + fi.diag.z * best.ip.z + fi.diag.w < 0) best.tri = fi.tri1;
+				if ((F & FRAY_F_ATTR) && (fi.flags & FRAY_FLAT_ATTR)) {
+					const DNode<R>& nd = sc.nodes[node];
+					flatBarycentrics(sc, nd, best.tri, best.ip, best.l2, best.l3);
+					triangleAttributes(sc, fi.mesh, best.tri, best.l2, best.l3, best.norm, best.u, best.v);
+					best.norm = xfDir(nd.T, best.norm);
+				}
+			}
 		}
 	}
-	for (int l = 0; l < sc.numLights; l++) {
-		R d;
-		if (intersectLight(sc.lights[l], ray, d) && d < best.dist) {
-			best.dist = d;
-			light = l;
+	if (F & FRAY_F_NODES) {
+		for (int n = 0; n < sc.numNodes; n++) {
+			if ((F & FRAY_F_FLAT) && sc.nodes[n].inFlat) continue;
+			Hit<R> h;
+			if (intersectNode<R, false, F>(sc, n, ray, best.dist, h) && h.dist < best.dist) {
+				best = h;
+				node = n;
+				light = -1;
+			}
+		}
+	}
+	if (!(F & FRAY_F_FLAT) || !sc.lightsInFlat) {
+		for (int l = 0; l < sc.numLights; l++) {
+			R d;
+			if (intersectLight(sc.lights[l], ray, d) && d < best.dist) {
+				best.dist = d;
+				light = l;
+			}
 		}
 	}
 }
@@ -877,10 +963,10 @@ FRAY_HD void lightSample(const DLight<R>& l, Rng& rng, int sampleIdx, const V3<R
 // Whitted shading: local terms (Lambert / Phong), src/shading.cpp:48-80, 101-144
 // ---------------------------------------------------------------------------------------------------
 template <typename R, int F>
-FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, Rng& rng, RayCounters& cnt)
+FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, Rng& rng, RayCounters& cnt)
 {
 	Col diffuse = loadCol(s.color);
-	if (s.texture >= 0) diffuse = diffuse * sampleTexture(sc, s.texture, rayDir, h.norm, h.u, h.v);
+	if ((F & FRAY_F_TEX) && s.texture >= 0) diffuse = diffuse * sampleTexture(sc, s.texture, rayDir, h.norm, h.u, h.v);
 	Col result = diffuse * loadCol(sc.ambient);
 	const V3<R> n = faceforward(rayDir, h.norm);
 	const V3<R> shadowStart = h.ip + n * Num<R>::offsetEps(maxAbs(h.ip));
@@ -898,7 +984,7 @@ FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const DShader<R>& s, const V3<
 			const float cosAngle = (float) dot(toLight, n);
 			float lambertTerm = (float) (cosAngle / distSqr);
 			lambertTerm = fmaxf(0.0f, lambertTerm);
-			if (visible<R, F>(sc, shadowStart, lightPos, cnt)) {
+			if (visible<R, F>(sc, ft, shadowStart, lightPos, cnt)) {
 				Col c = diffuse * lightCol * lambertTerm;
 				if (s.type == FRAY_SHADER_PHONG) {
 					const V3<R> r = reflect(-toLight, n);
@@ -955,14 +1041,14 @@ template <typename R> struct WhittedState {
 // "add weight * local shading now, push weight' * raytrace(child) for later". `spawn` numbers the children of this
 // raytrace() invocation in the order the reference would create them (RNG contract).
 template <typename R, int LEVEL, int F>
-FRAY_HD void shadeWhitted(const DScene<R>& sc, int shaderIdx, const V3<R>& rayDir, int depth, const Hit<R>& h, const Col& weight,
+FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx, const V3<R>& rayDir, int depth, const Hit<R>& h, const Col& weight,
                           Rng& rng, uint32_t& spawn, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
 	const DShader<R>& s = sc.shaders[shaderIdx];
 	switch (s.type) {
 		case FRAY_SHADER_CONST: accum = accum + weight * loadCol(s.color); return; // src/shading.cpp:35-38
 		case FRAY_SHADER_LAMBERT:
-		case FRAY_SHADER_PHONG: accum = accum + weight * shadeDirect<R, F>(sc, s, rayDir, h, rng, cnt); return;
+		case FRAY_SHADER_PHONG: accum = accum + weight * shadeDirect<R, F>(sc, ft, s, rayDir, h, rng, cnt); return;
 		case FRAY_SHADER_REFL: {
 			const V3<R> n = faceforward(rayDir, h.norm);
 			const V3<R> start = h.ip + n * Num<R>::offsetEps(maxAbs(h.ip));
@@ -1032,10 +1118,10 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, int shaderIdx, const V3<R>& rayDi
 				Col w = weight;
 				for (int j = nl - 1; j >= i; j--) {
 					const DLayer& L = sc.layers[s.firstLayer + j];
-					const Col op = L.texture >= 0 ? sampleTexture(sc, L.texture, rayDir, h.norm, h.u, h.v) : loadCol(L.opacity);
+					const Col op = ((F & FRAY_F_TEX) && L.texture >= 0) ? sampleTexture(sc, L.texture, rayDir, h.norm, h.u, h.v) : loadCol(L.opacity);
 					w = w * (j == i ? op : (Col(1, 1, 1) - op));
 				}
-				shadeWhitted<R, (LEVEL < 2 ? LEVEL + 1 : 2), F>(sc, sc.layers[s.firstLayer + i].shader, rayDir, depth, h, w, rng, spawn, ws, accum, cnt);
+				shadeWhitted<R, (LEVEL < 2 ? LEVEL + 1 : 2), F>(sc, ft, sc.layers[s.firstLayer + i].shader, rayDir, depth, h, w, rng, spawn, ws, accum, cnt);
 			}
 			return;
 		}
@@ -1045,7 +1131,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, int shaderIdx, const V3<R>& rayDi
 // raytrace(), src/main.cpp:246-285: one ray of the Whitted tree. Adds weight * (what this invocation returns minus
 // what its secondary rays return) to accum and pushes the secondary rays.
 template <typename R, int F>
-FRAY_HD void whittedStep(const DScene<R>& sc, const RayTask<R>& task, Rng& rng, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
+FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R>& task, Rng& rng, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
 	if (task.depth > sc.maxTraceDepth) return;
 	cnt.rays++;
@@ -1054,16 +1140,16 @@ FRAY_HD void whittedStep(const DScene<R>& sc, const RayTask<R>& task, Rng& rng, 
 	ray.dir = task.dir;
 	int node, light;
 	Hit<R> h;
-	closestHit<R, F>(sc, ray, node, light, h);
+	closestHit<R, F>(sc, ft, ray, node, light, h);
 	if (light >= 0) { accum = accum + task.weight * lightEmission(sc.lights[light]); return; }
 	if (node < 0) {
-		if (sc.hasEnv) accum = accum + task.weight * environmentLookup(sc, ray.dir);
+		if ((F & FRAY_F_TEX) && sc.hasEnv) accum = accum + task.weight * environmentLookup(sc, ray.dir);
 		return;
 	}
 	const DNode<R>& nd = sc.nodes[node];
-	applyBump(sc, nd, h);
+	if (F & FRAY_F_TEX) applyBump(sc, nd, h);
 	uint32_t spawn = 0;
-	shadeWhitted<R, 0, F>(sc, nd.shader, ray.dir, task.depth, h, task.weight, rng, spawn, ws, accum, cnt);
+	shadeWhitted<R, 0, F>(sc, ft, nd.shader, ray.dir, task.depth, h, task.weight, rng, spawn, ws, accum, cnt);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1093,7 +1179,7 @@ template <typename R> FRAY_HD V3<R> hemisphereSample(Rng& rng, const V3<R>& norm
 
 // One iteration of pathtrace(): returns false when the path ended. `accum` receives the terms the reference adds up
 // (contribLight of every level and the terminal term); FP32 summation order differs from the recursion's unwinding.
-template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, PathState<R>& ps, Rng& rng, Col& accum, RayCounters& cnt)
+template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, const FlatTab& ft, PathState<R>& ps, Rng& rng, Col& accum, RayCounters& cnt)
 {
 	if (ps.depth > sc.maxTraceDepth || ps.mult.intensity() <= 0.01f /* float < 0.01 (double) */) return false;
 	cnt.rays++;
@@ -1102,7 +1188,7 @@ template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, PathS
 	ray.dir = ps.dir;
 	int node, light;
 	Hit<R> h;
-	closestHit<R, F>(sc, ray, node, light, h);
+	closestHit<R, F>(sc, ft, ray, node, light, h);
 #if defined(FRAY_DEBUG_TRACE) && !defined(__CUDA_ARCH__)
 	printf("  seg depth %d start (%.6f %.6f %.6f) dir (%.6f %.6f %.6f) -> node %d light %d dist %.6f ip (%.5f %.5f %.5f) mult %.5f draws %u\n", ps.depth, (double) ray.start.x, (double) ray.start.y,
 	       (double) ray.start.z, (double) ray.dir.x, (double) ray.dir.y, (double) ray.dir.z, node, light, (double) h.dist, (double) h.ip.x, (double) h.ip.y, (double) h.ip.z, ps.mult.intensity(), rng.count);
@@ -1112,12 +1198,12 @@ template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, PathS
 		return false;
 	}
 	if (node < 0) {
-		if (sc.hasEnv) accum = accum + environmentLookup(sc, ray.dir) * ps.mult;
+		if ((F & FRAY_F_TEX) && sc.hasEnv) accum = accum + environmentLookup(sc, ray.dir) * ps.mult;
 		return false;
 	}
 	const DNode<R>& nd = sc.nodes[node];
 	const DShader<R>& s = sc.shaders[nd.shader];
-	applyBump(sc, nd, h);
+	if (F & FRAY_F_TEX) applyBump(sc, nd, h);
 	const R eps = Num<R>::offsetEps(maxAbs(h.ip));
 	const bool lambert = s.type == FRAY_SHADER_LAMBERT;
 
@@ -1150,7 +1236,7 @@ template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, PathS
 					brdfZero = false;
 				}
 				if (Num<R>::kExact || !brdfZero) {
-					const bool vis = visible<R, F>(sc, h.ip + h.norm * eps, onLight, cnt);
+					const bool vis = visible<R, F>(sc, ft, h.ip + h.norm * eps, onLight, cnt);
 					if (vis && !brdfZero) {
 						const float probHit = (float) (1.0f / solidAngle);
 						const float probPick = 1.0f / (float) sc.numLights;
@@ -1257,7 +1343,7 @@ FRAY_HD void sampleOffset(bool randomOffsets, int sampleIdx, Rng& rng, float& ox
 // through raytraceSinglePixel (src/main.cpp:304-321). Used by the AOV pass, the test emulator and as the
 // straight-line reference for the warp-scheduled kernels in render_kernels.cuh.
 template <typename R, int F>
-FRAY_HD Col renderSample(const DScene<R>& sc, uint32_t seed, int px, int py, int width, int sampleIdx, WhittedState<R>* ws, RayCounters& cnt)
+FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, int px, int py, int width, int sampleIdx, WhittedState<R>* ws, RayCounters& cnt)
 {
 	Rng rng;
 	rng.init(seed, (uint32_t) (py * width + px), (uint32_t) sampleIdx, 0);
@@ -1280,7 +1366,7 @@ FRAY_HD Col renderSample(const DScene<R>& sc, uint32_t seed, int px, int py, int
 			ps.mult = Col(1, 1, 1);
 			ps.depth = 0;
 			ps.flags = 0;
-			while (pathSegment<R, F>(sc, ps, rng, c, cnt)) {}
+			while (pathSegment<R, F>(sc, ft, ps, rng, c, cnt)) {}
 		} else {
 			ws->sp = 0;
 			RayTask<R> root;
@@ -1290,13 +1376,13 @@ FRAY_HD Col renderSample(const DScene<R>& sc, uint32_t seed, int px, int py, int
 			root.depth = 0;
 			root.branch = 0;
 			root.count = 0;
-			whittedStep<R, F>(sc, root, rng, *ws, c, cnt); // the primary invocation draws from the pixel sample's own stream
+			whittedStep<R, F>(sc, ft, root, rng, *ws, c, cnt); // the primary invocation draws from the pixel sample's own stream
 			while (ws->sp > 0) {
 				const RayTask<R> t = ws->stack[--ws->sp];
 				Rng child;
 				child.init(seed, rng.pixel, rng.sample, t.branch);
 				child.skip(t.count);
-				whittedStep<R, F>(sc, t, child, *ws, c, cnt);
+				whittedStep<R, F>(sc, ft, t, child, *ws, c, cnt);
 			}
 		}
 		if (stereo) {

@@ -1,0 +1,108 @@
+// flat.cuh -- the "flat polygon table": fast-precision (FP32) intersection of everything the reference tests by brute force.
+//
+// The reference walks the node list for every ray (/root/reference/src/main.cpp:178-199, 250-271 and visible(), :64-80):
+// per node it transforms the ray into object space (Node::intersect, src/geometry.cpp:196-208), rejects against the mesh
+// box (Mesh::intersect, src/mesh.cpp:144-165), loops over the triangles of meshes with <= 20 triangles
+// (src/mesh.cpp:85,154-158; Triangle::intersectFast, src/triangle.cpp:66-94) and afterwards tests the rectangular lights
+// (RectLight::intersect, src/lights.cpp:79-103). On a GPU that control flow is the cost: 32 incoherent rays of a warp
+// disagree at every box test and every early-out, and the small tables are fetched again by every ray.
+//
+// Here all of that geometry is brought into ONE table at upload time (scene_image.h, buildFlat):
+//   * every triangle of every brute-force mesh, transformed to WORLD space through its node's transform, so no per-node
+//     ray transform and no box test remain (a triangle hit implies the box hit);
+//   * two fan triangles of one OBJ face that are coplanar and form a convex quadrilateral are merged into one record
+//     (the union of the two acceptance regions is the quadrilateral), halving the work for quad meshes;
+//   * every RectLight as the world-space image of its unit square, facing the way src/lights.cpp:85-86 demands.
+// A record is a plane plus up to four inward edge planes (80 bytes, five float4):
+//     plane = (N, dN)          t = (dN - N.o) / (N.d)   hit point p = o + t d   front side: N.d < 0 (back-face culling,
+//                                                                               src/mesh.cpp:106; two-sided meshes get
+//                                                                               a second record with N reversed)
+//     edge_i = (m_i, c_i)      inside  <=>  m_i.p + c_i >= 0 for i = 0..3  (for a triangle these are the barycentrics
+//                                                                               lambda2, lambda3, 1-lambda2-lambda3 and 1)
+// The kernels stage the table in shared memory once per CTA; the loop below is branch-free, every lane of a warp walks the
+// same records (128-bit broadcast reads), and a ray costs ~40 issue slots per record whatever the other lanes do.
+// Attributes of the winning record (node, triangle ids, world shading normal) are looked up afterwards in FlatInfo.
+#pragma once
+#include <stdint.h>
+
+#if !defined(__CUDACC__)
+struct alignas(16) float4 { float x, y, z, w; };
+#endif
+
+namespace fray {
+
+#define FRAY_FLAT_POLY_VEC 5   // float4 per record
+#define FRAY_MAX_FLAT 96       // records staged per scene (7.5 KB of shared memory + 4.5 KB of FlatInfo)
+
+enum {
+	FRAY_FLAT_LIGHT = 1, // node = light index
+	FRAY_FLAT_ATTR = 2,  // the mesh interpolates normals and/or uvs: barycentrics are recomputed for the winner
+	FRAY_FLAT_QUAD = 4   // two triangles merged; `diag` tells them apart
+};
+
+struct FlatInfo {
+	float nx, ny, nz;   // world shading normal of a faceted record: normalize(gnormal * m), src/geometry.cpp:204, src/matrix.cpp:153-156
+	int node;           // node index (or light index when FRAY_FLAT_LIGHT)
+	int tri0, tri1;     // absolute triangle indices (tri1: the second triangle of a merged quad, else -1)
+	int mesh;
+	int flags;
+	float4 diag;        // FRAY_FLAT_QUAD: diag . (p, 1) < 0 <=> p lies in tri1
+};
+
+// closest record hit by the ray (o, d) with 0 <= t < tBest; `idx` is left alone when nothing is closer
+FRAY_HD void flatClosest(const float4* __restrict__ P, int n, float ox, float oy, float oz, float dx, float dy, float dz, float& tBest, int& idx)
+{
+#if defined(__CUDACC__)
+#pragma unroll 2
+#endif
+	for (int i = 0; i < n; i++) {
+		const float4 pl = P[FRAY_FLAT_POLY_VEC * i], e0 = P[FRAY_FLAT_POLY_VEC * i + 1], e1 = P[FRAY_FLAT_POLY_VEC * i + 2],
+		             e2 = P[FRAY_FLAT_POLY_VEC * i + 3], e3 = P[FRAY_FLAT_POLY_VEC * i + 4];
+		const float s = pl.x * dx + pl.y * dy + pl.z * dz;
+		const float h = pl.w - (pl.x * ox + pl.y * oy + pl.z * oz);
+#if defined(__CUDA_ARCH__)
+		const float t = __fdividef(h, s);
+#else
+		const float t = h / s;
+#endif
+		const float px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
+		const float a = e0.x * px + e0.y * py + e0.z * pz + e0.w;
+		const float b = e1.x * px + e1.y * py + e1.z * pz + e1.w;
+		const float c = e2.x * px + e2.y * py + e2.z * pz + e2.w;
+		const float e = e3.x * px + e3.y * py + e3.z * pz + e3.w;
+		const float inside = fminf(fminf(a, b), fminf(c, e));
+		const bool ok = (s < 0.0f) & (t >= 0.0f) & (t < tBest) & (inside >= 0.0f);
+		tBest = ok ? t : tBest;
+		idx = ok ? i : idx;
+	}
+}
+
+// is any record hit with 0 <= t < tMax ?
+FRAY_HD bool flatAny(const float4* __restrict__ P, int n, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
+{
+	bool hit = false;
+#if defined(__CUDACC__)
+#pragma unroll 2
+#endif
+	for (int i = 0; i < n; i++) {
+		const float4 pl = P[FRAY_FLAT_POLY_VEC * i], e0 = P[FRAY_FLAT_POLY_VEC * i + 1], e1 = P[FRAY_FLAT_POLY_VEC * i + 2],
+		             e2 = P[FRAY_FLAT_POLY_VEC * i + 3], e3 = P[FRAY_FLAT_POLY_VEC * i + 4];
+		const float s = pl.x * dx + pl.y * dy + pl.z * dz;
+		const float h = pl.w - (pl.x * ox + pl.y * oy + pl.z * oz);
+#if defined(__CUDA_ARCH__)
+		const float t = __fdividef(h, s);
+#else
+		const float t = h / s;
+#endif
+		const float px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
+		const float a = e0.x * px + e0.y * py + e0.z * pz + e0.w;
+		const float b = e1.x * px + e1.y * py + e1.z * pz + e1.w;
+		const float c = e2.x * px + e2.y * py + e2.z * pz + e2.w;
+		const float e = e3.x * px + e3.y * py + e3.z * pz + e3.w;
+		const float inside = fminf(fminf(a, b), fminf(c, e));
+		hit |= (s < 0.0f) & (t >= 0.0f) & (t < tMax) & (inside >= 0.0f);
+	}
+	return hit;
+}
+
+} // namespace fray

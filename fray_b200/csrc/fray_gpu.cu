@@ -293,7 +293,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 
 	int& occ = gi ? c->occGI : c->occWhitted;
 	if (occ < 0) {
-		occ = c->precision == FRAY_GPU_FP32 ? renderOccupancy<float>(c->features, gi) : renderOccupancy<double>(c->features, gi);
+		occ = c->precision == FRAY_GPU_FP32 ? renderOccupancy<float>(c->sc32, c->features, gi) : renderOccupancy<double>(c->sc64, c->features, gi);
 		if (occ < 1) occ = 1;
 	}
 	LaunchConfig cfg;

@@ -44,9 +44,28 @@ __device__ __forceinline__ Col shflXorCol(const Col& c, int m)
 	return Col(__shfl_xor_sync(0xffffffffu, c.r, m), __shfl_xor_sync(0xffffffffu, c.g, m), __shfl_xor_sync(0xffffffffu, c.b, m));
 }
 
+// Copies the flat polygon table (flat.cuh) into dynamic shared memory: 128-bit loads, once per CTA. The records of a scene
+// are read millions of times per CTA (every ray walks all of them), always by all lanes at once at the same address.
+template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const DScene<R>& sc)
+{
+	extern __shared__ float4 flatSmem[];
+	FlatTab ft;
+	ft.polys = flatSmem;
+	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatAll);
+	if (F & FRAY_F_FLAT) {
+		const int nPoly = FRAY_FLAT_POLY_VEC * sc.numFlatAll, nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * sc.numFlatAll;
+		const float4* gi = reinterpret_cast<const float4*>(sc.flatInfo);
+		for (int i = threadIdx.x; i < nPoly; i += blockDim.x) flatSmem[i] = sc.flatPolys[i];
+		for (int i = threadIdx.x; i < nInfo; i += blockDim.x) flatSmem[nPoly + i] = gi[i];
+		__syncthreads();
+	}
+	return ft;
+}
+
 template <typename R, bool GI, int F>
 __global__ void __launch_bounds__(128) renderKernel(const DScene<R> sc, const RenderParams p)
 {
+	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u;
 	const int G = p.lanesPerPixel;
 	const unsigned groupMask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(unsigned) (G - 1));
@@ -119,16 +138,16 @@ __global__ void __launch_bounds__(128) renderKernel(const DScene<R> sc, const Re
 			if (state == ACTIVE) {
 				bool finished;
 				if (GI) {
-					finished = !pathSegment<R, F>(sc, ps, rng, eyeCol, cnt);
+					finished = !pathSegment<R, F>(sc, ft, ps, rng, eyeCol, cnt);
 				} else {
 					const RayTask<R> t = ws.stack[--ws.sp];
 					if (t.branch == 0) {
-						whittedStep<R, F>(sc, t, rng, ws, eyeCol, cnt); // primary invocation: the sample's own stream
+						whittedStep<R, F>(sc, ft, t, rng, ws, eyeCol, cnt); // primary invocation: the sample's own stream
 					} else {
 						Rng child;
 						child.init(p.seed, rng.pixel, rng.sample, t.branch);
 						child.skip(t.count);
-						whittedStep<R, F>(sc, t, child, ws, eyeCol, cnt);
+						whittedStep<R, F>(sc, ft, t, child, ws, eyeCol, cnt);
 					}
 					finished = ws.sp == 0;
 				}
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(128) renderKernel(const DScene<R> sc, const Re
 template <typename R, int F>
 __global__ void __launch_bounds__(128) aovKernel(const DScene<R> sc, const RenderParams p)
 {
+	const FlatTab ft = stageFlat<R, F>(sc);
 	const int total = p.numBuckets * FRAY_BUCKET * FRAY_BUCKET;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
 		const int4 bk = p.buckets[i / (FRAY_BUCKET * FRAY_BUCKET)];
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(128) aovKernel(const DScene<R> sc, const Rende
 		const Ray<R> ray = screenRay(sc.cam, (R) px, (R) py, 0);
 		int node, light;
 		Hit<R> h;
-		closestHit<R, F>(sc, ray, node, light, h);
+		closestHit<R, F>(sc, ft, ray, node, light, h);
 		float* o = p.out + 3 * ((size_t) py * p.width + px);
 		o[0] = light >= 0 ? (float) (-2 - light) : (float) node;
 		o[1] = (light < 0 && node >= 0 && h.tri >= 0) ? (float) (h.tri - sc.meshes[h.mesh].firstTri) : -1.0f;
@@ -208,40 +228,49 @@ struct LaunchConfig {
 	cudaStream_t stream;
 };
 
+template <typename R> inline size_t flatSmemBytes(const DScene<R>& sc)
+{
+	return (size_t) sc.numFlatAll * (FRAY_FLAT_POLY_VEC * sizeof(float4) + sizeof(FlatInfo));
+}
+
 // one launch of the render (or AOV) kernel for precision R; defined in render_fp32.cu / render_fp64.cu
 template <typename R> cudaError_t launchRender(const DScene<R>& sc, const RenderParams& p, int features, int mode, const LaunchConfig& cfg);
-template <typename R> int renderOccupancy(int features, bool gi); // resident CTAs of 128 threads per SM
+template <typename R> int renderOccupancy(const DScene<R>& sc, int features, bool gi); // resident CTAs of 128 threads per SM
 
-template <typename R, bool GI, int F> cudaError_t launchOne(const DScene<R>& sc, const RenderParams& p, const LaunchConfig& cfg)
-{
-	renderKernel<R, GI, F><<<cfg.gridBlocks, 128, 0, cfg.stream>>>(sc, p);
-	return cudaGetLastError();
-}
+template <typename R, int I> struct VariantDispatch {
+	static constexpr int F = Variants<R>::mask(I);
+	static cudaError_t launch(const DScene<R>& sc, const RenderParams& p, int need, int mode, const LaunchConfig& cfg)
+	{
+		if ((need & ~F) != 0) return VariantDispatch<R, I + 1>::launch(sc, p, need, mode, cfg);
+		const size_t smem = (F & FRAY_F_FLAT) ? flatSmemBytes(sc) : 0;
+		if (mode == FRAY_RENDER_AOV) aovKernel<R, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
+		else if (sc.gi) renderKernel<R, true, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
+		else renderKernel<R, false, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
+		return cudaGetLastError();
+	}
+	static int occupancy(const DScene<R>& sc, int need, bool gi)
+	{
+		if ((need & ~F) != 0) return VariantDispatch<R, I + 1>::occupancy(sc, need, gi);
+		const size_t smem = (F & FRAY_F_FLAT) ? flatSmemBytes(sc) : 0;
+		int n = 0;
+		if (gi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, renderKernel<R, true, F>, 128, smem);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, renderKernel<R, false, F>, 128, smem);
+		return n;
+	}
+};
+template <typename R> struct VariantDispatch<R, Variants<R>::count> {
+	static cudaError_t launch(const DScene<R>&, const RenderParams&, int, int, const LaunchConfig&) { return cudaErrorInvalidValue; }
+	static int occupancy(const DScene<R>&, int, bool) { return 0; }
+};
 
 #define FRAY_DEFINE_LAUNCHERS(R)                                                                                              \
 	template <> cudaError_t launchRender<R>(const DScene<R>& sc, const RenderParams& p, int features, int mode, const LaunchConfig& cfg) \
 	{                                                                                                                         \
-		const bool csg = (features & FRAY_F_CSG) != 0;                                                                        \
-		if (mode == FRAY_RENDER_AOV) {                                                                                        \
-			if (csg) aovKernel<R, FRAY_F_CSG><<<cfg.gridBlocks, 128, 0, cfg.stream>>>(sc, p);                                 \
-			else aovKernel<R, 0><<<cfg.gridBlocks, 128, 0, cfg.stream>>>(sc, p);                                              \
-			return cudaGetLastError();                                                                                        \
-		}                                                                                                                     \
-		if (sc.gi) return csg ? launchOne<R, true, FRAY_F_CSG>(sc, p, cfg) : launchOne<R, true, 0>(sc, p, cfg);               \
-		return csg ? launchOne<R, false, FRAY_F_CSG>(sc, p, cfg) : launchOne<R, false, 0>(sc, p, cfg);                        \
+		return VariantDispatch<R, 0>::launch(sc, p, features, mode, cfg);                                                     \
 	}                                                                                                                         \
-	template <> int renderOccupancy<R>(int features, bool gi)                                                                 \
+	template <> int renderOccupancy<R>(const DScene<R>& sc, int features, bool gi)                                            \
 	{                                                                                                                         \
-		int n = 0;                                                                                                            \
-		const bool csg = (features & FRAY_F_CSG) != 0;                                                                        \
-		if (gi) {                                                                                                             \
-			if (csg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, renderKernel<R, true, FRAY_F_CSG>, 128, 0);            \
-			else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, renderKernel<R, true, 0>, 128, 0);                         \
-		} else {                                                                                                              \
-			if (csg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, renderKernel<R, false, FRAY_F_CSG>, 128, 0);           \
-			else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, renderKernel<R, false, 0>, 128, 0);                        \
-		}                                                                                                                     \
-		return n;                                                                                                             \
+		return VariantDispatch<R, 0>::occupancy(sc, features, gi);                                                            \
 	}
 
 } // namespace fray

@@ -10,6 +10,7 @@
 //   * relative indices -> absolute, identity transforms flagged, "does anything on this node read (u,v)" flagged
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,6 +75,188 @@ template <typename R> struct SceneImage {
 		int d = 0;
 		for (int i = 0; i < sh.num_layers; i++) d = std::max(d, layeredDepth(s, s.layers[sh.first_layer + i].shader, depth + 1));
 		return 1 + d;
+	}
+
+
+	// ---- flat polygon table (flat.cuh), fast precision only --------------------------------------------------------------
+	struct D3 { double x, y, z; };
+	static D3 sub(D3 a, D3 b) { return D3{ a.x - b.x, a.y - b.y, a.z - b.z }; }
+	static D3 crs(D3 a, D3 b) { return D3{ a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+	static double dt(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+	static D3 scl(D3 a, double m) { return D3{ a.x * m, a.y * m, a.z * m }; }
+	static D3 rowMul(D3 v, const double* m) // row vector times row-major 3x3 (src/matrix.h:53-60)
+	{
+		return D3{ v.x * m[0] + v.y * m[3] + v.z * m[6], v.x * m[1] + v.y * m[4] + v.z * m[7], v.x * m[2] + v.y * m[5] + v.z * m[8] };
+	}
+	static float4 plane4(D3 n, double c)
+	{
+		float4 r;
+		r.x = (float) n.x; r.y = (float) n.y; r.z = (float) n.z; r.w = (float) c;
+		return r;
+	}
+	// edge plane through a and b inside the polygon plane with normal n, scaled to 1 at `opposite` (inside = positive)
+	static bool edgePlane(D3 a, D3 b, D3 n, D3 opposite, float4& out, double* atOthers = nullptr, const D3* others = nullptr, int numOthers = 0)
+	{
+		D3 m = crs(n, sub(b, a));
+		double v = dt(m, sub(opposite, a));
+		if (v == 0) return false;
+		m = scl(m, 1 / v);
+		out = plane4(m, -dt(m, a));
+		for (int i = 0; i < numOthers; i++) atOthers[i] = dt(m, sub(others[i], a));
+		return true;
+	}
+
+	std::vector<float4> flatPolys;
+	std::vector<FlatInfo> flatInfo;
+
+	void pushFlat(const float4 rec[5], const FlatInfo& fi, bool twoSided)
+	{
+		for (int k = 0; k < 5; k++) flatPolys.push_back(rec[k]);
+		flatInfo.push_back(fi);
+		if (twoSided) { // the same polygon seen from behind: plane reversed, edges unchanged
+			float4 back = rec[0];
+			back.x = -back.x; back.y = -back.y; back.z = -back.z; back.w = -back.w;
+			flatPolys.push_back(back);
+			for (int k = 1; k < 5; k++) flatPolys.push_back(rec[k]);
+			flatInfo.push_back(fi);
+		}
+	}
+
+	// Fills flatPolys / flatInfo and marks the nodes whose geometry moved into the table. Returns the feature bits used.
+	int buildFlat(const FrayGpuScene& s, std::vector<DNode<R>>& nodes)
+	{
+		flatPolys.clear();
+		flatInfo.clear();
+		int feat = 0;
+		const float4 always = plane4(D3{ 0, 0, 0 }, 1.0);
+		int numRect = 0;
+		for (int i = 0; i < s.num_lights; i++) numRect += s.lights[i].type == FRAY_LIGHT_RECT;
+		if (numRect > FRAY_MAX_FLAT / 2) return 0; // absurd: leave everything to the generic loops
+		int room = FRAY_MAX_FLAT - numRect;
+
+		for (int ni = 0; ni < s.num_nodes; ni++) {
+			const FrayGpuNode& n = s.nodes[ni];
+			const FrayGpuGeometry& g = s.geometries[n.geometry];
+			if (g.type != FRAY_GEOM_MESH) continue;
+			const FrayGpuMesh& m = s.meshes[g.mesh];
+			if (m.kd_root >= 0 || m.num_triangles <= 0) continue;
+			const bool cull = (m.flags & FRAY_MESH_BACKFACE_CULL) != 0;
+			const bool smooth = !(m.flags & FRAY_MESH_FACETED) && (m.flags & FRAY_MESH_HAS_NORMALS);
+			const bool attr = smooth || ((m.flags & FRAY_MESH_HAS_UVS) && nodes[ni].needsUV) || n.bump >= 0;
+			const double* M = n.T.m;
+			const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+			if (det == 0) continue;
+			const D3 off{ n.T.offset[0], n.T.offset[1], n.T.offset[2] };
+			auto world = [&](int tri, int k) {
+				const double* v = s.vertices + 3 * ((size_t) m.first_vertex + s.tri_v[3 * ((size_t) m.first_triangle + tri) + k]);
+				const D3 p = rowMul(D3{ v[0], v[1], v[2] }, M);
+				return D3{ p.x + off.x, p.y + off.y, p.z + off.z };
+			};
+			// records of this node, built first so that a node is flattened completely or not at all
+			std::vector<float4> recs;
+			std::vector<FlatInfo> infos;
+			bool ok = true;
+			for (int t = 0; t < m.num_triangles && ok; t++) {
+				const size_t ti = (size_t) m.first_triangle + t;
+				const D3 A = world(t, 0), B = world(t, 1), C = world(t, 2);
+				D3 N = crs(sub(B, A), sub(C, A));
+				const double nn = dt(N, N);
+				if (!(nn > 0)) continue; // degenerate: |Dcr| < 1e-12 rejects it in the reference as well (src/triangle.cpp:72)
+				// reference culls on dot(dir_object, gnormal_object) > 0, i.e. against the TRUE world normal times sign(det)
+				const D3 Nf = det > 0 ? N : scl(N, -1);
+				FlatInfo fi;
+				memset(&fi, 0, sizeof(fi));
+				{ // shading normal of a faceted hit: normalize(gnormal * m) -- by m, not its inverse transpose (src/matrix.cpp:153-156)
+					const double* gn = s.tri_gnormal + 3 * ti;
+					D3 w = rowMul(D3{ gn[0], gn[1], gn[2] }, M);
+					const double l = sqrt(dt(w, w));
+					if (l > 0) w = scl(w, 1 / l);
+					fi.nx = (float) w.x; fi.ny = (float) w.y; fi.nz = (float) w.z;
+				}
+				fi.node = ni; fi.tri0 = (int) ti; fi.tri1 = -1; fi.mesh = g.mesh; fi.flags = attr ? FRAY_FLAT_ATTR : 0;
+				float4 rec[5];
+				rec[0] = plane4(Nf, dt(Nf, A));
+				rec[4] = always;
+				// try to merge with the next fan triangle (A, C, D) of the same face
+				bool merged = false;
+				if (!attr && t + 1 < m.num_triangles) {
+					const D3 A2 = world(t + 1, 0), C2 = world(t + 1, 1), Dq = world(t + 1, 2);
+					const double* g0 = s.tri_gnormal + 3 * ti;
+					const double* g1 = s.tri_gnormal + 3 * (ti + 1);
+					const bool sameA = A2.x == A.x && A2.y == A.y && A2.z == A.z && C2.x == C.x && C2.y == C.y && C2.z == C.z;
+					const bool sameNormal = g0[0] == g1[0] && g0[1] == g1[1] && g0[2] == g1[2]; // one shading normal for both halves
+					const double extent = sqrt(std::max(dt(sub(B, A), sub(B, A)), std::max(dt(sub(C, A), sub(C, A)), dt(sub(Dq, A), sub(Dq, A)))));
+					const double offPlane = fabs(dt(N, sub(Dq, A))) / sqrt(nn);
+					if (sameA && (sameNormal || offPlane <= 1e-9 * extent) && offPlane <= 1e-7 * extent) {
+						// convex quadrilateral A, B, C, D: every vertex on the inner side of every edge
+						const D3 P[4] = { A, B, C, Dq };
+						float4 e[4];
+						bool convex = true;
+						for (int k = 0; k < 4 && convex; k++) {
+							const D3 a = P[k], b = P[(k + 1) & 3];
+							const D3 others[2] = { P[(k + 2) & 3], P[(k + 3) & 3] };
+							double at[2];
+							// scale by the farther of the two remaining vertices
+							D3 mN = crs(N, sub(b, a));
+							const double v0 = dt(mN, sub(others[0], a)), v1 = dt(mN, sub(others[1], a));
+							if (!(v0 > 0 && v1 > 0)) { convex = false; break; }
+							convex = edgePlane(a, b, N, v0 > v1 ? others[0] : others[1], e[k], at, others, 2);
+						}
+						if (convex) {
+							for (int k = 0; k < 4; k++) rec[1 + k] = e[k];
+							fi.tri1 = (int) ti + 1;
+							fi.flags |= FRAY_FLAT_QUAD;
+							float4 dg; // positive on B's side of the diagonal A-C
+							if (edgePlane(A, C, N, B, dg)) {
+								fi.diag = dg;
+								merged = true;
+							}
+						}
+					}
+				}
+				if (!merged) {
+					fi.tri1 = -1;
+					fi.flags &= ~FRAY_FLAT_QUAD;
+					// barycentrics: lambda2 (0 on AC, 1 at B), lambda3 (0 on AB, 1 at C), lambda1 (0 on BC, 1 at A)
+					if (!edgePlane(A, C, N, B, rec[1]) || !edgePlane(A, B, N, C, rec[2]) || !edgePlane(B, C, N, A, rec[3])) continue;
+					rec[4] = always;
+				}
+				for (int k = 0; k < 5; k++) recs.push_back(rec[k]);
+				infos.push_back(fi);
+				if (merged) t++;
+			}
+			const int count = (int) infos.size() * (cull ? 1 : 2);
+			if (!ok || count > room) continue;
+			room -= count;
+			for (size_t k = 0; k < infos.size(); k++) pushFlat(&recs[5 * k], infos[k], !cull);
+			nodes[ni].inFlat = 1;
+			feat |= FRAY_F_FLAT;
+			if (attr) feat |= FRAY_F_ATTR;
+		}
+		offsets.numFlatGeom = (int) flatInfo.size();
+		// lights: the unit square of light space, seen from its -y side by rays travelling towards +y (src/lights.cpp:79-103)
+		for (int li = 0; li < s.num_lights; li++) {
+			const FrayGpuLight& l = s.lights[li];
+			if (l.type != FRAY_LIGHT_RECT) continue;
+			const double* I = l.T.inv;
+			const D3 off{ l.T.offset[0], l.T.offset[1], l.T.offset[2] };
+			const D3 cx{ I[0], I[3], I[6] }, cy{ I[1], I[4], I[7] }, cz{ I[2], I[5], I[8] }; // columns: x_l(p) = (p - off) . cx
+			float4 rec[5];
+			const D3 Nf = scl(cy, -1);
+			rec[0] = plane4(Nf, dt(Nf, off));
+			rec[1] = plane4(scl(cx, -1), 0.5 + dt(cx, off));
+			rec[2] = plane4(cx, 0.5 - dt(cx, off));
+			rec[3] = plane4(scl(cz, -1), 0.5 + dt(cz, off));
+			rec[4] = plane4(cz, 0.5 - dt(cz, off));
+			FlatInfo fi;
+			memset(&fi, 0, sizeof(fi));
+			fi.node = li; fi.tri0 = fi.tri1 = -1; fi.mesh = -1; fi.flags = FRAY_FLAT_LIGHT;
+			pushFlat(rec, fi, false);
+			feat |= FRAY_F_FLAT;
+		}
+		offsets.numFlatAll = (int) flatInfo.size();
+		offsets.lightsInFlat = 1;
+		return feat;
 	}
 
 	bool build(const FrayGpuScene& s, std::string& err)
@@ -270,7 +453,17 @@ template <typename R> struct SceneImage {
 			cvtXform(o.T, n.T);
 			o.geom = n.geometry; o.shader = n.shader; o.bump = n.bump;
 			o.needsUV = shaderReadsUV(s, n.shader, 0) || textureReadsUV(s, n.bump);
+			o.inFlat = 0;
+			o.pad[0] = o.pad[1] = o.pad[2] = 0;
 		}
+		// feature bits this scene needs from the kernels
+		if (s.num_textures > 0 || s.has_environment) features |= FRAY_F_TEX;
+		for (int i = 0; i < s.num_nodes; i++)
+			if (s.nodes[i].bump >= 0) features |= FRAY_F_TEX;
+		if (!Num<R>::kExact) features |= buildFlat(s, nodes);
+		for (int i = 0; i < s.num_nodes; i++)
+			if (!nodes[i].inFlat) features |= FRAY_F_NODES;
+		if (Num<R>::kExact) features |= FRAY_F_GENERIC;
 		std::vector<R> normals(3 * (size_t) s.num_normals), uvs(3 * (size_t) s.num_uvs);
 		for (size_t i = 0; i < normals.size(); i++) normals[i] = (R) s.normals[i];
 		for (size_t i = 0; i < uvs.size(); i++) uvs[i] = (R) s.uvs[i];
@@ -300,6 +493,8 @@ template <typename R> struct SceneImage {
 		FRAY_PUT(kdBox, kdBox);
 		FRAY_PUT(leafRefs, leafRefs);
 		FRAY_PUT(texels, texels);
+		FRAY_PUT(flatPolys, flatPolys);
+		FRAY_PUT(flatInfo, flatInfo);
 #undef FRAY_PUT
 		return true;
 	}
@@ -315,6 +510,7 @@ template <typename R> struct SceneImage {
 		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
 		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
 		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
+		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo);
 #undef FRAY_REBASE
 		return d;
 	}

@@ -15,7 +15,7 @@
 using namespace fray;
 
 template <typename R, int F>
-static void renderRows(const DScene<R>& sc, const FrayGpuFrame& fr, int W, int H, int spp, int s0, int s1, float* out,
+static void renderRows(const DScene<R>& sc, const FlatTab& ft, const FrayGpuFrame& fr, int W, int H, int spp, int s0, int s1, float* out,
                        std::atomic<int>& nextRow, RayCounters& total)
 {
 	WhittedState<R>* ws = new WhittedState<R>;
@@ -34,14 +34,14 @@ static void renderRows(const DScene<R>& sc, const FrayGpuFrame& fr, int W, int H
 				Ray<R> ray = screenRay(sc.cam, (R) x, (R) y, 0);
 				int node, light;
 				Hit<R> h;
-				closestHit<R, F>(sc, ray, node, light, h);
+				closestHit<R, F>(sc, ft, ray, node, light, h);
 				o[0] = light >= 0 ? (float) (-2 - light) : (float) node;
 				o[1] = (light < 0 && node >= 0 && h.tri >= 0) ? (float) (h.tri - sc.meshes[h.mesh].firstTri) : -1.0f;
 				o[2] = (float) h.dist;
 				continue;
 			}
 			Col sum(0, 0, 0);
-			for (int i = s0; i < s1; i++) sum = sum + renderSample<R, F>(sc, fr.seed, x, y, W, i, ws, cnt);
+			for (int i = s0; i < s1; i++) sum = sum + renderSample<R, F>(sc, ft, fr.seed, x, y, W, i, ws, cnt);
 			if (!(fr.flags & FRAY_FRAME_SUM)) sum = sum / (float) spp;
 			o[0] = sum.r; o[1] = sum.g; o[2] = sum.b;
 		}
@@ -68,9 +68,15 @@ static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out
 	std::atomic<int> nextRow(0);
 	RayCounters total = { 0, 0, 0 };
 	std::vector<std::thread> pool;
-	auto run = [&]() {
-		if (img.features & FRAY_F_CSG) renderRows<R, FRAY_F_CSG>(sc, *fr, W, H, spp, s0, s1, out, nextRow, total);
-		else renderRows<R, 0>(sc, *fr, W, H, spp, s0, s1, out, nextRow, total);
+	FlatTab ft;
+	ft.polys = sc.flatPolys;
+	ft.info = sc.flatInfo;
+	const int need = img.features;
+	auto run = [&]() { // the same variant selection as VariantDispatch in render_kernels.cuh
+		if (Variants<R>::count > 0 && (need & ~Variants<R>::mask(0)) == 0) renderRows<R, Variants<R>::mask(0)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else if (Variants<R>::count > 1 && (need & ~Variants<R>::mask(1)) == 0) renderRows<R, Variants<R>::mask(1)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else if (Variants<R>::count > 2 && (need & ~Variants<R>::mask(2)) == 0) renderRows<R, Variants<R>::mask(2)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else renderRows<R, Variants<R>::mask(3)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 	};
 	for (int t = 1; t < threads; t++) pool.emplace_back(run);
 	run();

@@ -19,7 +19,7 @@ EMUL_DIR = os.path.join(fb.REPO_ROOT, "tests", "emul")
 def emul():
     so = os.path.join(EMUL_DIR, "libfray_emul.so")
     src = os.path.join(EMUL_DIR, "kernel_emul.cpp")
-    deps = [src] + [os.path.join(fb.REPO_ROOT, "fray_b200", "csrc", f) for f in ("core.cuh", "rng.cuh", "scene_image.h")]
+    deps = [src] + [os.path.join(fb.REPO_ROOT, "fray_b200", "csrc", f) for f in ("core.cuh", "flat.cuh", "rng.cuh", "scene_image.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-x", "c++", src,
                                "-o", so, "-lpthread"])
