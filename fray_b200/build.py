@@ -69,7 +69,7 @@ def build_gpu(force: bool = False, verbose_ptxas: bool = False) -> str:
     out = os.path.join(HERE, "libfray_gpu.so")
     os.makedirs(BUILD, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in ("core.cuh", "flat.cuh", "rng.cuh", "render_kernels.cuh", "scene_image.h")] + [os.path.join(INCLUDE, "fray_gpu.h")]
-    units = [("fray_gpu.cu", []), ("render_fp32.cu", []), ("render_fp64.cu", ["-fmad=false"])]
+    units = [("fray_gpu.cu", []), ("render_fp32.cu", ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]), ("render_fp64.cu", ["-fmad=false"])]
     extra = ["-Xptxas", "-v"] if verbose_ptxas else []
     jobs = []
     for src, flags in units:

@@ -267,7 +267,9 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	memset(&p, 0, sizeof(p));
 	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
 	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
-	const int G = std::min(32, pow2Floor(std::max(1, s1 - s0)));
+	// lanes per pixel: every lane should own >= ~32 samples so that the drain at the end of a warp task (lanes running dry
+	// while the longest path of the pixel tile finishes) stays a few percent of the task
+	const int G = std::min(32, pow2Floor(std::max(1, (s1 - s0) / 32)));
 	p.lanesPerPixel = G;
 	const int P = 32 / G; // pixels per warp task: 32 -> 8x4, 16 -> 4x4, 8 -> 4x2, 4 -> 2x2, 2 -> 2x1, 1 -> 1x1
 	p.tileW = P >= 32 ? 8 : (P >= 8 ? 4 : (P >= 2 ? 2 : 1));

@@ -175,7 +175,8 @@ template <typename R> struct SceneImage {
 				}
 				fi.node = ni; fi.tri0 = (int) ti; fi.tri1 = -1; fi.mesh = g.mesh; fi.flags = attr ? FRAY_FLAT_ATTR : 0;
 				float4 rec[5];
-				rec[0] = plane4(Nf, dt(Nf, A));
+				const D3 Nu = scl(Nf, 1 / sqrt(nn)); // unit plane normal: N.d is the cosine, t is world distance
+				rec[0] = plane4(Nu, dt(Nu, A));
 				rec[4] = always;
 				// try to merge with the next fan triangle (A, C, D) of the same face
 				bool merged = false;
@@ -242,7 +243,7 @@ template <typename R> struct SceneImage {
 			const D3 off{ l.T.offset[0], l.T.offset[1], l.T.offset[2] };
 			const D3 cx{ I[0], I[3], I[6] }, cy{ I[1], I[4], I[7] }, cz{ I[2], I[5], I[8] }; // columns: x_l(p) = (p - off) . cx
 			float4 rec[5];
-			const D3 Nf = scl(cy, -1);
+			const D3 Nf = scl(cy, -1 / sqrt(dt(cy, cy)));
 			rec[0] = plane4(Nf, dt(Nf, off));
 			rec[1] = plane4(scl(cx, -1), 0.5 + dt(cx, off));
 			rec[2] = plane4(cx, 0.5 - dt(cx, off));
