@@ -1177,11 +1177,19 @@ template <typename R> FRAY_HD V3<R> hemisphereSample(Rng& rng, const V3<R>& norm
 	return dot(d, norm) > 0 ? d : -d;
 }
 
+// the cut-off at the top of pathtrace(), src/main.cpp:173-176
+template <typename R> FRAY_HD bool pathAlive(const DScene<R>& sc, const PathState<R>& ps)
+{
+	return !(ps.depth > sc.maxTraceDepth || ps.mult.intensity() <= 0.01f /* float < 0.01 (double) */);
+}
+
 // One iteration of pathtrace(): returns false when the path ended. `accum` receives the terms the reference adds up
 // (contribLight of every level and the terminal term); FP32 summation order differs from the recursion's unwinding.
+// The cut-off of the NEXT level is evaluated at the end of this one, so that a lane whose path is over learns it in
+// the same iteration and never spends a whole trip round the warp loop just to find out.
 template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, const FlatTab& ft, PathState<R>& ps, Rng& rng, Col& accum, RayCounters& cnt)
 {
-	if (ps.depth > sc.maxTraceDepth || ps.mult.intensity() <= 0.01f /* float < 0.01 (double) */) return false;
+	if (!pathAlive(sc, ps)) return false; // only the first level can fail here (maxTraceDepth < 0)
 	cnt.rays++;
 	Ray<R> ray;
 	ray.start = ps.start;
@@ -1284,7 +1292,7 @@ template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, const
 	}
 	ps.depth++;
 	ps.mult = ps.mult * brdf / pdf;
-	return true;
+	return pathAlive(sc, ps);
 }
 
 // ---------------------------------------------------------------------------------------------------
