@@ -1,0 +1,170 @@
+// main.cpp -- the `fray [--gpu] scene.fray` entry point (host side of the B200 back end).
+//
+// Mirrors main() of the reference (/root/reference/src/main.cpp:494-530): parse the command line (exit -1 on a usage
+// error, :414-424), check the scene file (exit -2, :498-501), parse it (exit -3, :503-506), beginRender(), render one frame
+// and report "Render took %.2fs" (:517-520). Where the reference opens an SDL window and waits for F12 to write a
+// screenshot (src/sdl.cpp:101-160), this tool is headless and writes the frame to --out (BMP or EXR, the two formats
+// Bitmap::saveImage knows, src/bitmap.cpp:197-284). The frame itself is produced by libfray_gpu.so through the C ABI of
+// include/fray_gpu.h -- loaded with dlopen so that the host layer has no link-time CUDA dependency. There is no CPU
+// renderer in this build: without --gpu (or without a CUDA device) the tool says so and fails.
+//
+//   fray --gpu [--fp64] [--out frame.bmp] [--seed N] [--spp N] [--device D] [--frames K]
+//        [--bucket-rank R --bucket-count C] [--samples A:B] [--aov] [-v] scene.fray
+//
+// --bucket-* and --samples render one shard of the frame (tile split / sample split, include/fray_gpu.h FrayGpuFrame) so
+// that an outer launcher can spread a frame over several GPUs; fray_b200/dist.py does that with one process per GPU and an
+// NCCL reduce.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/fray_host.h"
+
+namespace {
+
+struct GpuApi {
+	void* handle = nullptr;
+	uint32_t (*abi_version)(void) = nullptr;
+	int (*device_count)(void) = nullptr;
+	int (*create)(const FrayGpuScene*, int, int, FrayGpuCtx**) = nullptr;
+	int (*render)(FrayGpuCtx*, const FrayGpuFrame*, float*, FrayGpuStats*) = nullptr;
+	void (*destroy)(FrayGpuCtx*) = nullptr;
+	const char* (*last_error)(void) = nullptr;
+};
+
+std::string exeDir()
+{
+	char buf[4096];
+	ssize_t n = readlink("/proc/self/exe", buf, sizeof(buf) - 1);
+	if (n <= 0) return ".";
+	buf[n] = 0;
+	char* slash = strrchr(buf, '/');
+	if (slash) *slash = 0;
+	return buf;
+}
+
+bool loadGpu(GpuApi& api, std::string& err)
+{
+	const std::string beside = exeDir() + "/libfray_gpu.so";
+	api.handle = dlopen(beside.c_str(), RTLD_NOW | RTLD_LOCAL);
+	if (!api.handle) api.handle = dlopen("libfray_gpu.so", RTLD_NOW | RTLD_LOCAL);
+	if (!api.handle) {
+		err = dlerror();
+		return false;
+	}
+#define FRAY_SYM(member, name)                                              \
+	api.member = reinterpret_cast<decltype(api.member)>(dlsym(api.handle, name)); \
+	if (!api.member) { err = std::string("missing symbol ") + name; return false; }
+	FRAY_SYM(abi_version, "fray_gpu_abi_version");
+	FRAY_SYM(device_count, "fray_gpu_device_count");
+	FRAY_SYM(create, "fray_gpu_create");
+	FRAY_SYM(render, "fray_gpu_render");
+	FRAY_SYM(destroy, "fray_gpu_destroy");
+	FRAY_SYM(last_error, "fray_gpu_last_error");
+#undef FRAY_SYM
+	if (api.abi_version() != FRAY_GPU_ABI_VERSION) {
+		err = "libfray_gpu.so has a different ABI version";
+		return false;
+	}
+	return true;
+}
+
+void usage() { fprintf(stderr, "Usage: fray --gpu [--fp64] [--out file.bmp|.exr] [--seed N] [--spp N] [--device D] [--frames K]\n"
+                               "            [--bucket-rank R --bucket-count C] [--samples A:B] [--aov] [-v] scene.fray\n"); }
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+	bool gpu = false, verbose = false, aov = false;
+	int precision = FRAY_GPU_FP32, device = 0, frames = 1;
+	FrayGpuFrame frame;
+	memset(&frame, 0, sizeof(frame));
+	frame.seed = 42; // initRandom(42), src/main.cpp:502
+	std::string out, sceneFile = "data/boxed.fray"; // default scene of the reference, src/main.cpp:51
+	for (int i = 1; i < argc; i++) {
+		const std::string a = argv[i];
+		auto next = [&](const char* what) -> const char* {
+			if (i + 1 >= argc) { fprintf(stderr, "fray: %s needs a value\n", what); usage(); exit(-1); }
+			return argv[++i];
+		};
+		if (a == "--gpu") gpu = true;
+		else if (a == "--fp64") precision = FRAY_GPU_FP64;
+		else if (a == "-v") verbose = true;
+		else if (a == "--aov") aov = true;
+		else if (a == "--out") out = next("--out");
+		else if (a == "--seed") frame.seed = (uint32_t) strtoul(next("--seed"), nullptr, 10);
+		else if (a == "--spp") frame.spp = atoi(next("--spp"));
+		else if (a == "--device") device = atoi(next("--device"));
+		else if (a == "--frames") frames = atoi(next("--frames"));
+		else if (a == "--bucket-rank") frame.bucket_rank = atoi(next("--bucket-rank"));
+		else if (a == "--bucket-count") frame.bucket_count = atoi(next("--bucket-count"));
+		else if (a == "--samples") {
+			if (sscanf(next("--samples"), "%d:%d", &frame.sample_begin, &frame.sample_end) != 2) { usage(); return -1; }
+		} else if (!a.empty() && a[0] == '-') { usage(); return -1; }
+		else sceneFile = a;
+	}
+	if (!gpu) {
+		fprintf(stderr, "fray: this build contains only the CUDA back end; run it as `fray --gpu %s`\n", sceneFile.c_str());
+		return -1;
+	}
+	struct stat st;
+	if (stat(sceneFile.c_str(), &st) != 0) {
+		fprintf(stderr, "The specified scene file does not exist: %s", sceneFile.c_str());
+		return -2;
+	}
+	fray_host_set_verbose(verbose ? 1 : 0);
+	FrayHostScene* scene = fray_host_load_scene(sceneFile.c_str());
+	if (!scene) {
+		fprintf(stderr, "%s\n", fray_host_last_error());
+		return -3;
+	}
+	const FrayGpuScene* flat = fray_host_flat_scene(scene);
+	const int W = flat->settings.frame_width, H = flat->settings.frame_height;
+
+	GpuApi api;
+	std::string err;
+	if (!loadGpu(api, err)) {
+		fprintf(stderr, "fray: cannot load the CUDA back end: %s\n", err.c_str());
+		return -4;
+	}
+	FrayGpuCtx* ctx = nullptr;
+	if (api.create(flat, device, precision, &ctx) != FRAY_GPU_OK) {
+		fprintf(stderr, "fray: %s\n", api.last_error());
+		return -4;
+	}
+	if (aov) frame.mode = FRAY_RENDER_AOV;
+	std::vector<float> rgb((size_t) W * H * 3);
+	FrayGpuStats stats;
+	memset(&stats, 0, sizeof(stats));
+	for (int f = 0; f < frames; f++) {
+		const auto t0 = std::chrono::steady_clock::now();
+		if (api.render(ctx, &frame, rgb.data(), &stats) != FRAY_GPU_OK) {
+			fprintf(stderr, "fray: %s\n", api.last_error());
+			api.destroy(ctx);
+			return -5;
+		}
+		const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		printf("Render took %.2fs\n", sec); // src/main.cpp:519
+		if (verbose)
+			printf("  %dx%d, %llu rays (%llu primary, %llu shadow), device %.3f ms, %.1f Mrays/s\n", W, H, (unsigned long long) stats.rays,
+			       (unsigned long long) stats.primary_rays, (unsigned long long) stats.shadow_rays, stats.device_ms,
+			       stats.device_ms > 0 ? stats.rays / stats.device_ms / 1e3 : 0.0);
+	}
+	int rc = 0;
+	if (!out.empty() && fray_host_save_image(out.c_str(), rgb.data(), W, H) != 0) {
+		fprintf(stderr, "fray: cannot write %s: %s\n", out.c_str(), fray_host_last_error());
+		rc = -6;
+	}
+	api.destroy(ctx);
+	fray_host_free_scene(scene);
+	if (rc == 0) printf("Exited cleanly\n");
+	return rc;
+}

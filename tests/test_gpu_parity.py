@@ -188,3 +188,23 @@ def test_full_size_properties_cornell(data_dir):
     rmse_halves = np.sqrt((((a - b) / 128.0) ** 2).mean())
     assert 0.01 < rmse_halves < 0.2
     ctx.close()
+
+
+def test_cli_renders_and_writes_bmp(tmp_path, data_dir):
+    """`fray --gpu scene.fray --out frame.bmp`: the entry point, end to end, against the library call it wraps."""
+    import subprocess
+    import fray_b200.build as fbuild
+    exe = fbuild.build_cli()
+    scene_file = ou.override_scene("cornell_box", "cli", dict(frameWidth=64, frameHeight=48, pathsPerPixel=8))
+    out = str(tmp_path / "frame.bmp")
+    r = subprocess.run([exe, "--gpu", "-v", "--out", out, scene_file], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Render took" in r.stdout and "Exited cleanly" in r.stdout
+    sc = fb.Scene(scene_file)
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    want, _ = ctx.render(seed=42)
+    ctx.close()
+    got = fb.load_image(out)
+    assert got.shape == want.shape
+    # 8-bit BMP: nearestInt(clamp01(x) * 255), src/color.h:29-34,59-66
+    np.testing.assert_allclose(got, np.round(np.clip(want, 0, 1) * 255) / 255, atol=1e-6)

@@ -163,3 +163,31 @@ def test_exr_writer_roundtrip(tmp_path):
     fb.save_image(p, rgb)
     back = fb.load_image(p)
     assert np.array_equal(back, rgb.astype(np.float16).astype(np.float32))  # HALF storage, round to nearest even
+
+
+# ---- the `fray` command line tool (fray_b200/host/main.cpp), the parts that need no GPU ----
+def _cli():
+    import fray_b200.build as fbuild
+    fbuild.build_host()
+    exe = fbuild.build_cli()
+    assert exe and os.path.exists(exe)
+    return exe
+
+
+def test_cli_exit_codes_follow_the_reference(tmp_path, data_dir):
+    """src/main.cpp:494-506: -1 usage error, -2 missing scene file, -3 parse error (as 8-bit exit statuses)."""
+    import subprocess
+    exe = _cli()
+    scene = os.path.join(data_dir, "cornell_box.fray")
+    r = subprocess.run([exe, scene], capture_output=True, text=True)          # no --gpu: this build has no CPU renderer
+    assert r.returncode == 255 and "--gpu" in r.stderr
+    r = subprocess.run([exe, "--gpu", "--bogus", scene], capture_output=True, text=True)
+    assert r.returncode == 255 and "Usage" in r.stderr
+    r = subprocess.run([exe, "--gpu", str(tmp_path / "missing.fray")], capture_output=True, text=True)
+    assert r.returncode == 254 and "does not exist" in r.stderr
+    bad = write(tmp_path, "bad.fray", "Camera camera {\n\tposition (0, 0, 0)\n")   # unterminated block
+    r = subprocess.run([exe, "--gpu", bad], capture_output=True, text=True)
+    assert r.returncode == 253
+    if fb.gpu_lib().fray_gpu_device_count() == 0:
+        r = subprocess.run([exe, "--gpu", scene], capture_output=True, text=True)
+        assert r.returncode == 252 and "no CPU fallback" in r.stderr
