@@ -221,10 +221,10 @@ def main():
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     kernel_ms = []
     rays_step = 0
-    barrier()
     if sampler:
         sampler.start()
         time.sleep(0.25)
+    barrier()  # after the sampler's start-up delay on rank 0, so that all ranks enter the timed region together
     t0 = time.time()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed frames (not timed)
@@ -238,6 +238,8 @@ def main():
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    if os.environ.get("FRAY_BENCH_DEBUG"):
+        log(f"rank {rank}: step_ms {[round(x, 3) for x in step_ms]} kernel_ms {[round(x, 3) for x in kernel_ms]} wall {t1 - t0:.3f}s")
     tot = torch.tensor([sum(step_ms), float(rays_step), sum(kernel_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tot.clone()

@@ -250,10 +250,12 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	const int brank = f->bucket_count > 0 ? f->bucket_rank : 0;
 	if (brank < 0 || brank >= bcount) return fail(FRAY_GPU_EINVAL, "bucket_rank outside [0, bucket_count)");
 
-	std::vector<int4> all, owned;
+	// Tile split: every call gets the whole bucket list; ownership is decided per WARP TASK (a pixel tile of a bucket, see
+	// render_kernels.cuh): task t of the frame belongs to share t % bucket_count. Thousands of small interleaved tiles per
+	// share balance the load far better than whole 48x48 buckets (81 of them in a 400x400 frame).
+	std::vector<int4> all;
 	bucketList(c->width, c->height, all);
-	for (size_t i = 0; i < all.size(); i++)
-		if ((int) (i % bcount) == brank) owned.push_back(all[i]);
+	const std::vector<int4>& owned = all;
 	if ((int) owned.size() > c->bucketCapacity) {
 		cudaFree(c->dBuckets);
 		c->dBuckets = nullptr;
@@ -277,12 +279,14 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	p.numBuckets = (int) owned.size();
 	p.buckets = c->dBuckets;
 	p.totalTasks = p.numBuckets * (FRAY_BUCKET / p.tileW) * (FRAY_BUCKET / p.tileH);
+	p.taskStride = bcount;
+	p.taskOffset = brank;
 	p.out = dOut;
 	p.counters = c->dCounters;
 	p.workCounter = c->dWork;
 	p.errorFlag = c->dError;
 
-	if (owned.size() != all.size()) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
+	if (bcount > 1) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
 	if (!owned.empty() && (c->cachedBucketCount != bcount || c->cachedBucketRank != brank || c->cachedOwned != (int) owned.size())) {
 		CUDA_TRY(cudaMemcpyAsync(c->dBuckets, owned.data(), owned.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream)); // `owned` is a pageable temporary
@@ -309,7 +313,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 		                                                : launchRender<double>(c->sc64, p, c->features, f->mode, cfg);
 		if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
 		c->launches = 1;
-	} else if (owned.size() == all.size()) {
+	} else if (bcount == 1) {
 		CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
 	}
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStop, stream));

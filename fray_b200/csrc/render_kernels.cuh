@@ -30,7 +30,8 @@ struct RenderParams {
 	int tileW, tileH; // pixel tile of one warp task, tileW * tileH * G == 32
 	int numBuckets;   // owned buckets
 	const int4* buckets; // x0, y0, w, h
-	int totalTasks;
+	int totalTasks;   // warp tasks of the whole frame
+	int taskStride, taskOffset; // this call owns the tasks t with t % taskStride == taskOffset (multi-GPU tile split)
 	float* out;       // [height][width][3]
 	unsigned long long* counters; // rays, primary, shadow
 	unsigned int* workCounter;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : 1) renderK
 	for (;;) {
 		unsigned task = 0;
 		if (lane == 0) task = atomicAdd(p.workCounter, 1u);
-		task = __shfl_sync(0xffffffffu, task, 0);
+		task = __shfl_sync(0xffffffffu, task, 0) * (unsigned) p.taskStride + (unsigned) p.taskOffset;
 		if (task >= (unsigned) p.totalTasks) break;
 
 		const int4 bk = p.buckets[task / tilesPerBucket];
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(128) aovKernel(const DScene<R> sc, const Rende
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const int total = p.numBuckets * FRAY_BUCKET * FRAY_BUCKET;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		if ((i / 32) % p.taskStride != p.taskOffset) continue; // shards own interleaved runs of 32 pixels
 		const int4 bk = p.buckets[i / (FRAY_BUCKET * FRAY_BUCKET)];
 		const int k = i % (FRAY_BUCKET * FRAY_BUCKET);
 		const int lx = k % FRAY_BUCKET, ly = k / FRAY_BUCKET;

@@ -265,8 +265,9 @@ typedef struct FrayGpuFrame {
 	uint32_t seed;          /* initRandom() seed, 42 in src/main.cpp:502 */
 	int32_t sample_begin;   /* this call renders samples [sample_begin, sample_end) of every owned pixel; */
 	int32_t sample_end;     /*   0,0 = all */
-	int32_t bucket_rank;    /* this call owns the 48x48 buckets b of the serpentine list                  */
-	int32_t bucket_count;   /*   (src/sdl.cpp:243-262) with b % bucket_count == bucket_rank; 0,0 = all     */
+	int32_t bucket_rank;    /* this call owns share `bucket_rank` of `bucket_count` of the frame: the 48x48 buckets of   */
+	int32_t bucket_count;   /*   the serpentine list (src/sdl.cpp:243-262) are cut into small pixel tiles and tile t     */
+	                        /*   belongs to share t % bucket_count (disjoint, interleaved over the image); 0,0 = all      */
 	int32_t mode;           /* FRAY_RENDER_* */
 	uint32_t flags;         /* FRAY_FRAME_* */
 } FrayGpuFrame;

@@ -124,8 +124,15 @@ def override_scene(name: str, tag: str, settings: dict | None = None, camera: di
         ins = "".join(f"\n\t{k} {v}" for k, v in props.items())
         text = text[:m.end()] + ins + text[m.end():]
     dst = os.path.join(os.path.dirname(src), f"{os.path.basename(name)}__{tag}.fray")
-    with open(dst, "w") as f:
+    # several ranks of one torchrun job ask for the same file at the same time: never expose a half-written one
+    if os.path.exists(dst):
+        with open(dst) as f:
+            if f.read() == text:
+                return dst
+    tmp = f"{dst}.{os.getpid()}.tmp"
+    with open(tmp, "w") as f:
         f.write(text)
+    os.replace(tmp, dst)
     return dst
 
 
