@@ -234,6 +234,7 @@ def main():
         st = r.stats()  # syncs; per-step kernel time + ray counters of this rank
         kernel_ms.append(st.device_ms)
         rays_step = st.rays
+        launches_step = st.kernel_launches + (1 if rank == 0 else 0)  # render (+ combine) kernels, and the resolve kernel on rank 0
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -301,7 +302,7 @@ def main():
                        "split": r.mode if world > 1 else "none", "l2": "flushed between timed frames (256 MB write)", "seed": 42},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * 12},
-            "gpu_launches": args.steps * 2,  # renderKernel + resolveKernel per frame (rank 0)
+            "gpu_launches": args.steps * launches_step,  # renderKernel + combineKernel + resolveKernel per frame (rank 0)
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -45,9 +45,8 @@ struct FrayGpuCtx {
 	void* dBlob = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
-	int4* dBuckets = nullptr;
-	int bucketCapacity = 0;
-	int cachedBucketCount = -1, cachedBucketRank = -1, cachedOwned = 0; // what dBuckets currently holds
+	float* dScratch = nullptr;   // chunk sums of the current call (numChunks > 1)
+	size_t scratchFloats = 0;
 	unsigned long long* dCounters = nullptr; // 3 counters
 	unsigned int* dWork = nullptr;
 	int* dError = nullptr;
@@ -63,6 +62,22 @@ struct FrayGpuCtx {
 __global__ void resolveKernel(const float* __restrict__ sum, float* __restrict__ rgb, size_t n, float spp)
 {
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) rgb[i] = sum[i] / spp;
+}
+
+// numChunks > 1: pixel = sum of its chunk sums in chunk order (then / spp unless FRAY_FRAME_SUM)
+__global__ void combineKernel(const RenderParams p)
+{
+	const unsigned slots = (unsigned) p.numOwnedTiles * 32u;
+	for (unsigned slot = blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += gridDim.x * blockDim.x) {
+		int px, py;
+		if (!slotPixel(p, slot, px, py)) continue;
+		const float* c = p.scratch + 3 * (size_t) slot * p.numChunks;
+		Col sum(0, 0, 0);
+		for (int k = 0; k < p.numChunks; k++) sum = sum + Col(c[3 * k], c[3 * k + 1], c[3 * k + 2]);
+		if (!p.sumOnly) sum = sum / (float) p.spp;
+		float* o = p.out + 3 * ((size_t) py * p.width + px);
+		o[0] = sum.r; o[1] = sum.g; o[2] = sum.b;
+	}
 }
 
 // ---- roofline denominators ---------------------------------------------------------------------------
@@ -126,7 +141,7 @@ void fray_gpu_destroy(FrayGpuCtx* c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	cudaFree(c->dBlob);
-	cudaFree(c->dBuckets);
+	cudaFree(c->dScratch);
 	cudaFree(c->dCounters);
 	cudaFree(c->dWork);
 	cudaFree(c->dError);
@@ -209,24 +224,6 @@ int fray_gpu_update_camera(FrayGpuCtx* c, const FrayGpuCamera* cam)
 	return FRAY_GPU_OK;
 }
 
-// serpentine bucket list, src/sdl.cpp:243-262
-static void bucketList(int W, int H, std::vector<int4>& out)
-{
-	const int B = FRAY_BUCKET;
-	const int BW = (W - 1) / B + 1, BH = (H - 1) / B + 1;
-	out.clear();
-	for (int y = 0; y < BH; y++)
-		for (int i = 0; i < BW; i++) {
-			const int x = (y % 2 == 0) ? i : BW - 1 - i;
-			int4 r;
-			r.x = x * B;
-			r.y = y * B;
-			r.z = (x + 1) * B < W ? B : W - x * B;
-			r.w = (y + 1) * B < H ? B : H - y * B;
-			out.push_back(r);
-		}
-}
-
 static int pow2Floor(int v)
 {
 	int p = 1;
@@ -250,52 +247,10 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	const int brank = f->bucket_count > 0 ? f->bucket_rank : 0;
 	if (brank < 0 || brank >= bcount) return fail(FRAY_GPU_EINVAL, "bucket_rank outside [0, bucket_count)");
 
-	// Tile split: every call gets the whole bucket list; ownership is decided per WARP TASK (a pixel tile of a bucket, see
-	// render_kernels.cuh): task t of the frame belongs to share t % bucket_count. Thousands of small interleaved tiles per
-	// share balance the load far better than whole 48x48 buckets (81 of them in a 400x400 frame).
-	std::vector<int4> all;
-	bucketList(c->width, c->height, all);
-	const std::vector<int4>& owned = all;
-	if ((int) owned.size() > c->bucketCapacity) {
-		cudaFree(c->dBuckets);
-		c->dBuckets = nullptr;
-		c->bucketCapacity = 0;
-		CUDA_TRY(cudaMalloc(&c->dBuckets, all.size() * sizeof(int4)));
-		c->bucketCapacity = (int) all.size();
-		c->cachedBucketCount = -1;
-	}
-
-	RenderParams p;
-	memset(&p, 0, sizeof(p));
-	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
-	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
-	// lanes per pixel: every lane should own >= ~32 samples so that the drain at the end of a warp task (lanes running dry
-	// while the longest path of the pixel tile finishes) stays a few percent of the task
-	const int G = std::min(32, pow2Floor(std::max(1, (s1 - s0) / 32)));
-	p.lanesPerPixel = G;
-	const int P = 32 / G; // pixels per warp task: 32 -> 8x4, 16 -> 4x4, 8 -> 4x2, 4 -> 2x2, 2 -> 2x1, 1 -> 1x1
-	p.tileW = P >= 32 ? 8 : (P >= 8 ? 4 : (P >= 2 ? 2 : 1));
-	p.tileH = P / p.tileW;
-	p.numBuckets = (int) owned.size();
-	p.buckets = c->dBuckets;
-	p.totalTasks = p.numBuckets * (FRAY_BUCKET / p.tileW) * (FRAY_BUCKET / p.tileH);
-	p.taskStride = bcount;
-	p.taskOffset = brank;
-	p.out = dOut;
-	p.counters = c->dCounters;
-	p.workCounter = c->dWork;
-	p.errorFlag = c->dError;
-
-	if (bcount > 1) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
-	if (!owned.empty() && (c->cachedBucketCount != bcount || c->cachedBucketRank != brank || c->cachedOwned != (int) owned.size())) {
-		CUDA_TRY(cudaMemcpyAsync(c->dBuckets, owned.data(), owned.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
-		CUDA_TRY(cudaStreamSynchronize(stream)); // `owned` is a pageable temporary
-		c->cachedBucketCount = bcount;
-		c->cachedBucketRank = brank;
-		c->cachedOwned = (int) owned.size();
-	}
-	CUDA_TRY(cudaMemsetAsync(c->dCounters, 0, 3 * sizeof(unsigned long long), stream));
-	CUDA_TRY(cudaMemsetAsync(c->dWork, 0, sizeof(unsigned int), stream));
+	// work decomposition (render_kernels.cuh): 8x4 pixel tiles, tile t belongs to share t % bcount; samples in chunks of C
+	const int tilesX = (c->width + FRAY_TILE_W - 1) / FRAY_TILE_W, tilesY = (c->height + FRAY_TILE_H - 1) / FRAY_TILE_H;
+	const int totalTiles = tilesX * tilesY;
+	const int ownedTiles = totalTiles > brank ? (totalTiles - brank + bcount - 1) / bcount : 0;
 
 	int& occ = gi ? c->occGI : c->occWhitted;
 	if (occ < 0) {
@@ -306,13 +261,57 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	cfg.stream = stream;
 	cfg.gridBlocks = c->numSMs * occ; // persistent: every resident CTA slot of the chip, exactly once
 	if (f->mode == FRAY_RENDER_AOV) cfg.gridBlocks = c->numSMs * 8;
+
+	RenderParams p;
+	memset(&p, 0, sizeof(p));
+	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
+	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
+	// chunk size: every lane of the grid should see >= ~12 items, so that the drain at the end of the kernel (lanes running
+	// dry while the last items finish) is a few percent; at most 64 chunks per pixel bound the scratch buffer
+	const int samples = std::max(1, s1 - s0);
+	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) cfg.gridBlocks * 128.0);
+	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 12.0)));
+	C = std::max(C, (samples + 63) / 64);
+	C = std::min(C, samples);
+	p.chunk = C;
+	p.numChunks = (samples + C - 1) / C;
+	p.tilesX = tilesX;
+	p.numOwnedTiles = ownedTiles;
+	p.taskStride = bcount;
+	p.taskOffset = brank;
+	p.totalItems = (unsigned) ownedTiles * 32u * (unsigned) p.numChunks;
+	p.out = dOut;
+	p.counters = c->dCounters;
+	p.workCounter = c->dWork;
+	p.errorFlag = c->dError;
+	if (p.numChunks > 1) {
+		const size_t need = (size_t) ownedTiles * 32 * p.numChunks * 3;
+		if (need > c->scratchFloats) {
+			cudaFree(c->dScratch);
+			c->dScratch = nullptr;
+			c->scratchFloats = 0;
+			CUDA_TRY(cudaMalloc(&c->dScratch, need * sizeof(float)));
+			c->scratchFloats = need;
+		}
+		p.scratch = c->dScratch;
+	}
+
+	if (bcount > 1) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
+	CUDA_TRY(cudaMemsetAsync(c->dCounters, 0, 3 * sizeof(unsigned long long), stream));
+	CUDA_TRY(cudaMemsetAsync(c->dWork, 0, sizeof(unsigned int), stream));
+
 	c->launches = 0;
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStart, stream));
-	if (p.totalTasks > 0 && (s1 > s0 || f->mode == FRAY_RENDER_AOV)) {
+	if (ownedTiles > 0 && (s1 > s0 || f->mode == FRAY_RENDER_AOV)) {
 		cudaError_t e = c->precision == FRAY_GPU_FP32 ? launchRender<float>(c->sc32, p, c->features, f->mode, cfg)
 		                                                : launchRender<double>(c->sc64, p, c->features, f->mode, cfg);
 		if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
 		c->launches = 1;
+		if (p.numChunks > 1 && f->mode != FRAY_RENDER_AOV) {
+			combineKernel<<<c->numSMs * 4, 256, 0, stream>>>(p);
+			CUDA_TRY(cudaGetLastError());
+			c->launches = 2;
+		}
 	} else if (bcount == 1) {
 		CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
 	}

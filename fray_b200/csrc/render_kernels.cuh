@@ -1,17 +1,19 @@
 // render_kernels.cuh -- the sm_100a kernels that replace RendMT::entry (/root/reference/src/main.cpp:323-371).
 //
-// Scheduling model ("persistent warps with path regeneration"):
-//   * the frame is cut into the reference's 48x48 buckets (src/sdl.cpp:243-262); a call owns a subset of them
-//     (multi-GPU tile split) and a sample range [s0, s1) of every owned pixel (multi-GPU sample split);
-//   * a WARP TASK is a small pixel tile of one bucket: 32/G pixels, G lanes per pixel (G = 1..32, a power of two chosen
-//     from the number of samples). Persistent CTAs (grid = SMs x resident CTAs) pull warp tasks from one global
-//     counter, one atomic per task (warp-aggregated: lane 0 fetches, __shfl broadcasts);
-//   * inside a task every lane runs a state machine: whenever its path (GI) or ray tree (Whitted) is finished it takes
-//     the next unstarted sample of its pixel - the lanes of a pixel agree on who takes which sample with one
-//     __ballot_sync + popc per iteration - so lanes stay busy although paths end after different numbers of bounces
-//     (divergence per bounce is bounded by one segment instead of one whole path);
-//   * per-lane partial sums are combined with a fixed-order __shfl_xor tree, so a pixel is a pure function of
-//     (scene, seed, sample range): no float atomics, run-to-run bit-identical.
+// Scheduling model ("persistent lanes, two-level work queue, path regeneration"):
+//   * the frame is cut into 8x4 pixel tiles (row-major over the image); a call owns the tiles t with
+//     t % taskStride == taskOffset (multi-GPU tile split) and a sample range [s0, s1) of every owned pixel (sample split);
+//   * the samples of a pixel are cut into CHUNKS of C consecutive samples. A WORK ITEM is (owned pixel, chunk); item ids are
+//     laid out so that 32 consecutive ids are the 32 pixels of one tile for one chunk (coherent primary rays);
+//   * persistent CTAs (grid = SMs x resident CTAs). Every LANE owns one item at a time and is a state machine: whenever
+//     its path (GI) or ray tree (Whitted) is finished it starts the next sample of its item, and when the item is used up it
+//     writes the chunk's sum and takes the next item. Items come from a warp-level pool (a contiguous id range in uniform
+//     registers; lanes that need one agree by __ballot_sync + popc) which lane 0 refills 32 ids at a time with ONE atomicAdd
+//     on the global counter. No lane ever waits for another lane's path, pixel or tile; the only drain is at the very end
+//     of the kernel, and it is bounded by one item (C is chosen so that a lane sees >= ~12 items per call);
+//   * a chunk's sum is accumulated in sample order by one lane; chunk sums go to a scratch buffer and combineKernel adds
+//     them per pixel in chunk order (with one chunk per pixel the lane writes the pixel directly). A pixel is therefore a pure
+//     function of (scene, seed, sample range, C): no float atomics, run-to-run bit-identical.
 // The per-ray work itself is core.cuh.
 #pragma once
 #include <cuda_runtime.h>
@@ -20,29 +22,37 @@
 
 namespace fray {
 
+#define FRAY_TILE_W 8
+#define FRAY_TILE_H 4
+#define FRAY_POOL_BATCH 32 // item ids fetched per atomic
+
 struct RenderParams {
 	int width, height;
 	int spp;          // samples per pixel of the whole frame (divisor)
 	int s0, s1;       // sample range rendered by this call
 	uint32_t seed;
 	int sumOnly;      // FRAY_FRAME_SUM
-	int lanesPerPixel;// G
-	int tileW, tileH; // pixel tile of one warp task, tileW * tileH * G == 32
-	int numBuckets;   // owned buckets
-	const int4* buckets; // x0, y0, w, h
-	int totalTasks;   // warp tasks of the whole frame
-	int taskStride, taskOffset; // this call owns the tasks t with t % taskStride == taskOffset (multi-GPU tile split)
+	int chunk;        // C: samples per work item
+	int numChunks;    // ceil((s1 - s0) / C)
+	int tilesX;       // tiles per image row
+	int numOwnedTiles;
+	int taskStride, taskOffset; // owned tile j is tile j * taskStride + taskOffset of the frame
+	unsigned int totalItems;    // numOwnedTiles * 32 * numChunks
 	float* out;       // [height][width][3]
+	float* scratch;   // numChunks > 1: [owned pixel slot][chunk][3]
 	unsigned long long* counters; // rays, primary, shadow
 	unsigned int* workCounter;
 	int* errorFlag;
 };
 
-#define FRAY_BUCKET 48
-
-__device__ __forceinline__ Col shflXorCol(const Col& c, int m)
+// owned pixel slot (owned tile j, position in tile) -> pixel; false outside the image (border tiles)
+__device__ __forceinline__ bool slotPixel(const RenderParams& p, unsigned slot, int& px, int& py)
 {
-	return Col(__shfl_xor_sync(0xffffffffu, c.r, m), __shfl_xor_sync(0xffffffffu, c.g, m), __shfl_xor_sync(0xffffffffu, c.b, m));
+	const unsigned j = slot >> 5, within = slot & 31u;
+	const unsigned t = j * (unsigned) p.taskStride + (unsigned) p.taskOffset;
+	px = (int) (t % (unsigned) p.tilesX) * FRAY_TILE_W + (int) (within % FRAY_TILE_W);
+	py = (int) (t / (unsigned) p.tilesX) * FRAY_TILE_H + (int) (within / FRAY_TILE_W);
+	return px < p.width && py < p.height;
 }
 
 // Copies the flat polygon table (flat.cuh) into dynamic shared memory: 128-bit loads, once per CTA. The records of a scene
@@ -68,11 +78,7 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : 1) renderK
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u;
-	const int G = p.lanesPerPixel;
-	const unsigned groupMask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(unsigned) (G - 1));
 	const unsigned ltMask = (1u << lane) - 1u;
-	const int pixInWarp = (int) lane / G;
-	const int tilesX = FRAY_BUCKET / p.tileW, tilesPerBucket = tilesX * (FRAY_BUCKET / p.tileH);
 	const bool randomOffsets = sc.cam.dof || sc.gi;
 	const bool stereo = sc.cam.stereoSep > 0;
 
@@ -81,109 +87,130 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : 1) renderK
 	ws.sp = 0;
 	ws.overflow = 0;
 
+	// warp-level item pool [poolNext, poolEnd): identical in all lanes
+	unsigned poolNext = 0, poolEnd = 0;
+	bool exhausted = false; // the global counter ran past totalItems (warp-uniform)
+
+	// lane state
+	bool hasItem = false, active = false;
+	int px = 0, py = 0;
+	unsigned outIndex = 0; // where the chunk sum goes: pixel index (one chunk) or scratch index
+	int cur = 0, end = 0;  // next sample / end of the chunk
+	Col accum(0, 0, 0);    // sum over the finished samples of the chunk
+	Col eyeCol(0, 0, 0);   // radiance of the path / ray tree in flight
+	Rng rng;               // stream of the sample in flight (branch 0)
+	PathState<R> ps;
+	Ray<R> rightEye;       // stereo: the second ray is generated up front (src/main.cpp:307-308) and traced afterwards
+	int eye = 0;
+
 	for (;;) {
-		unsigned task = 0;
-		if (lane == 0) task = atomicAdd(p.workCounter, 1u);
-		task = __shfl_sync(0xffffffffu, task, 0) * (unsigned) p.taskStride + (unsigned) p.taskOffset;
-		if (task >= (unsigned) p.totalTasks) break;
+		// ---- lanes without a running sample: next sample of the item, or next item --------------------------------------
+		if (!active && hasItem && cur == end) { // chunk finished: write its sum
+			float* o;
+			if (p.numChunks == 1) {
+				o = p.out + 3 * (size_t) outIndex;
+				if (!p.sumOnly) accum = accum / (float) p.spp; // `avg / samplesPerPixel`, src/main.cpp:360
+			} else {
+				o = p.scratch + 3 * (size_t) outIndex;
+			}
+			o[0] = accum.r; o[1] = accum.g; o[2] = accum.b;
+			hasItem = false;
+		}
+		bool want = !active && !hasItem;
+		unsigned wanters = __ballot_sync(0xffffffffu, want);
+		while (wanters != 0 && !exhausted) {
+			if (poolNext == poolEnd) { // refill: one atomic per FRAY_POOL_BATCH items per warp
+				unsigned base = 0;
+				if (lane == 0) base = atomicAdd(p.workCounter, (unsigned) FRAY_POOL_BATCH);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (base >= p.totalItems) { exhausted = true; break; }
+				poolNext = base;
+				poolEnd = min(base + (unsigned) FRAY_POOL_BATCH, p.totalItems);
+			}
+			const unsigned avail = poolEnd - poolNext;
+			const unsigned rank = __popc(wanters & ltMask);
+			if (want && rank < avail) {
+				const unsigned id = poolNext + rank;
+				// id = (ownedTile * numChunks + chunk) * 32 + within
+				const unsigned within = id & 31u, tc = id >> 5;
+				const unsigned chunk = tc % (unsigned) p.numChunks, j = tc / (unsigned) p.numChunks;
+				const unsigned slot = (j << 5) | within;
+				if (slotPixel(p, slot, px, py)) {
+					hasItem = true;
+					cur = p.s0 + (int) chunk * p.chunk;
+					end = min(cur + p.chunk, p.s1);
+					accum = Col(0, 0, 0);
+					outIndex = p.numChunks == 1 ? (unsigned) (py * p.width + px) : slot * (unsigned) p.numChunks + chunk;
+				}
+				want = false; // a slot outside the image is simply dropped; the lane asks again next round
+			}
+			poolNext += min(avail, (unsigned) __popc(wanters));
+			wanters = __ballot_sync(0xffffffffu, want && !hasItem);
+		}
+		if (!active && hasItem && cur < end) { // start sample `cur`
+			const int s = cur++;
+			rng.init(p.seed, (uint32_t) (py * p.width + px), (uint32_t) s, 0);
+			float ox, oy;
+			sampleOffset(randomOffsets, s, rng, ox, oy);
+			const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);
+			Ray<R> first = cameraRay(sc.cam, rng, fx, fy, stereo ? 1 : 0);
+			if (stereo) rightEye = cameraRay(sc.cam, rng, fx, fy, 2);
+			eye = 0;
+			eyeCol = Col(0, 0, 0);
+			cnt.primary++;
+			if (GI) {
+				ps.start = first.start; ps.dir = first.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
+			} else {
+				RayTask<R> root;
+				root.start = first.start; root.dir = first.dir; root.weight = Col(1, 1, 1);
+				root.depth = 0; root.branch = 0; root.count = 0;
+				ws.stack[0] = root;
+				ws.sp = 1;
+			}
+			active = true;
+		}
+		if (exhausted && __all_sync(0xffffffffu, !active && !hasItem)) break;
 
-		const int4 bk = p.buckets[task / tilesPerBucket];
-		const int tile = task % tilesPerBucket;
-		const int lx = (tile % tilesX) * p.tileW + pixInWarp % p.tileW;
-		const int ly = (tile / tilesX) * p.tileH + pixInWarp / p.tileW;
-		const bool valid = lx < bk.z && ly < bk.w;
-		const int px = bk.x + lx, py = bk.y + ly;
-
-		enum { IDLE, ACTIVE, DONE };
-		int state = valid ? IDLE : DONE;
-		int next = p.s0;     // first unstarted sample of this lane's pixel (identical in all lanes of the group)
-		Col accum(0, 0, 0);  // sum over the samples this lane finished
-		Col eyeCol(0, 0, 0); // radiance of the path / ray tree in flight
-		Rng rng;             // stream of the sample in flight (branch 0)
-		PathState<R> ps;
-		Ray<R> rightEye;     // stereo: the second ray is generated up front (src/main.cpp:307-308) and traced afterwards
-		int eye = 0;
-
-		for (;;) {
-			const bool need = state == IDLE;
-			const unsigned ballot = __ballot_sync(0xffffffffu, need);
-			if (need) {
-				const int s = next + __popc(ballot & groupMask & ltMask);
-				if (s < p.s1) {
-					rng.init(p.seed, (uint32_t) (py * p.width + px), (uint32_t) s, 0);
-					float ox, oy;
-					sampleOffset(randomOffsets, s, rng, ox, oy);
-					const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);
-					Ray<R> first = cameraRay(sc.cam, rng, fx, fy, stereo ? 1 : 0);
-					if (stereo) rightEye = cameraRay(sc.cam, rng, fx, fy, 2);
-					eye = 0;
+		// ---- one path segment / one ray of the Whitted tree ---------------------------------------------------------------
+		if (active) {
+			bool finished;
+			if (GI) {
+				finished = !pathSegment<R, F>(sc, ft, ps, rng, eyeCol, cnt);
+			} else {
+				const RayTask<R> t = ws.stack[--ws.sp];
+				if (t.branch == 0) {
+					whittedStep<R, F>(sc, ft, t, rng, ws, eyeCol, cnt); // primary invocation: the sample's own stream
+				} else {
+					Rng child;
+					child.init(p.seed, rng.pixel, rng.sample, t.branch);
+					child.skip(t.count);
+					whittedStep<R, F>(sc, ft, t, child, ws, eyeCol, cnt);
+				}
+				finished = ws.sp == 0;
+			}
+			if (finished) {
+				if (stereo) {
+					if (sc.saturation != 1) eyeCol = adjustSaturation(eyeCol, sc.saturation);
+					eyeCol = eyeCol * (eye == 0 ? loadCol(sc.cam.leftMask) : loadCol(sc.cam.rightMask));
+				}
+				accum = accum + eyeCol;
+				if (stereo && eye == 0) {
+					eye = 1;
 					eyeCol = Col(0, 0, 0);
 					cnt.primary++;
 					if (GI) {
-						ps.start = first.start; ps.dir = first.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
+						ps.start = rightEye.start; ps.dir = rightEye.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
 					} else {
 						RayTask<R> root;
-						root.start = first.start; root.dir = first.dir; root.weight = Col(1, 1, 1);
+						root.start = rightEye.start; root.dir = rightEye.dir; root.weight = Col(1, 1, 1);
 						root.depth = 0; root.branch = 0; root.count = 0;
 						ws.stack[0] = root;
 						ws.sp = 1;
 					}
-					state = ACTIVE;
 				} else {
-					state = DONE;
+					active = false;
 				}
 			}
-			next += __popc(ballot & groupMask);
-			if (__all_sync(0xffffffffu, state == DONE)) break;
-
-			if (state == ACTIVE) {
-				bool finished;
-				if (GI) {
-					finished = !pathSegment<R, F>(sc, ft, ps, rng, eyeCol, cnt);
-				} else {
-					const RayTask<R> t = ws.stack[--ws.sp];
-					if (t.branch == 0) {
-						whittedStep<R, F>(sc, ft, t, rng, ws, eyeCol, cnt); // primary invocation: the sample's own stream
-					} else {
-						Rng child;
-						child.init(p.seed, rng.pixel, rng.sample, t.branch);
-						child.skip(t.count);
-						whittedStep<R, F>(sc, ft, t, child, ws, eyeCol, cnt);
-					}
-					finished = ws.sp == 0;
-				}
-				if (finished) {
-					if (stereo) {
-						if (sc.saturation != 1) eyeCol = adjustSaturation(eyeCol, sc.saturation);
-						eyeCol = eyeCol * (eye == 0 ? loadCol(sc.cam.leftMask) : loadCol(sc.cam.rightMask));
-					}
-					accum = accum + eyeCol;
-					if (stereo && eye == 0) {
-						eye = 1;
-						eyeCol = Col(0, 0, 0);
-						cnt.primary++;
-						if (GI) {
-							ps.start = rightEye.start; ps.dir = rightEye.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
-						} else {
-							RayTask<R> root;
-							root.start = rightEye.start; root.dir = rightEye.dir; root.weight = Col(1, 1, 1);
-							root.depth = 0; root.branch = 0; root.count = 0;
-							ws.stack[0] = root;
-							ws.sp = 1;
-						}
-					} else {
-						state = IDLE;
-					}
-				}
-			}
-		}
-
-		// fixed-order tree over the G lanes of the pixel
-		for (int m = G >> 1; m > 0; m >>= 1) accum = accum + shflXorCol(accum, m);
-		if (valid && (lane & (unsigned) (G - 1)) == 0) {
-			if (!p.sumOnly) accum = accum / (float) p.spp; // `avg / samplesPerPixel`, src/main.cpp:360
-			float* o = p.out + 3 * ((size_t) py * p.width + px);
-			o[0] = accum.r; o[1] = accum.g; o[2] = accum.b;
 		}
 	}
 
@@ -206,14 +233,10 @@ template <typename R, int F>
 __global__ void __launch_bounds__(128) aovKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
-	const int total = p.numBuckets * FRAY_BUCKET * FRAY_BUCKET;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-		if ((i / 32) % p.taskStride != p.taskOffset) continue; // shards own interleaved runs of 32 pixels
-		const int4 bk = p.buckets[i / (FRAY_BUCKET * FRAY_BUCKET)];
-		const int k = i % (FRAY_BUCKET * FRAY_BUCKET);
-		const int lx = k % FRAY_BUCKET, ly = k / FRAY_BUCKET;
-		if (lx >= bk.z || ly >= bk.w) continue;
-		const int px = bk.x + lx, py = bk.y + ly;
+	const unsigned slots = (unsigned) p.numOwnedTiles * 32u;
+	for (unsigned slot = blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += gridDim.x * blockDim.x) {
+		int px, py;
+		if (!slotPixel(p, slot, px, py)) continue;
 		const Ray<R> ray = screenRay(sc.cam, (R) px, (R) py, 0);
 		int node, light;
 		Hit<R> h;

@@ -265,9 +265,9 @@ typedef struct FrayGpuFrame {
 	uint32_t seed;          /* initRandom() seed, 42 in src/main.cpp:502 */
 	int32_t sample_begin;   /* this call renders samples [sample_begin, sample_end) of every owned pixel; */
 	int32_t sample_end;     /*   0,0 = all */
-	int32_t bucket_rank;    /* this call owns share `bucket_rank` of `bucket_count` of the frame: the 48x48 buckets of   */
-	int32_t bucket_count;   /*   the serpentine list (src/sdl.cpp:243-262) are cut into small pixel tiles and tile t     */
-	                        /*   belongs to share t % bucket_count (disjoint, interleaved over the image); 0,0 = all      */
+	int32_t bucket_rank;    /* this call owns share `bucket_rank` of `bucket_count` of the image: the frame is cut into  */
+	int32_t bucket_count;   /*   8x4 pixel tiles (row-major) and tile t belongs to share t % bucket_count -- the         */
+	                        /*   multi-GPU form of the reference's bucket list (src/sdl.cpp:243-262); 0,0 = all          */
 	int32_t mode;           /* FRAY_RENDER_* */
 	uint32_t flags;         /* FRAY_FRAME_* */
 } FrayGpuFrame;

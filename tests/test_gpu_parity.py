@@ -42,7 +42,7 @@ def test_fp64_matches_oracle_everywhere(name, scenes):
     frac, rmse, mx = ou.compare(want, got, 2e-5)
     assert frac == 1.0, (frac, rmse, mx)
     assert stats.rays == ostats.rays and stats.shadow_rays == ostats.shadow_rays and stats.primary_rays == ostats.primary_rays
-    assert stats.kernel_launches == 1
+    assert stats.kernel_launches in (1, 2)  # the render kernel (+ combineKernel when a pixel's samples are cut into chunks)
     waov, _ = ou.oracle_render(sc, mode=fb.RENDER_AOV)
     gaov, _ = ctx.render(mode=fb.RENDER_AOV)
     assert np.array_equal(gaov[..., :2], waov[..., :2])          # node and triangle ids
