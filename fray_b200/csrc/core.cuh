@@ -242,6 +242,11 @@ template <typename R> struct DScene {
 	int numFlatGeom;           // polygons [0, numFlatGeom) are node geometry (occluders)
 	int numFlatAll;            // polygons [numFlatGeom, numFlatAll) are lights
 	int lightsInFlat;          // the rectangular lights are in the table: the light loop of closestHit is skipped
+	// Shadow sets: the records that can occlude a ray towards light l at all, i.e. whose plane has some point of the light
+	// behind it (a ray hits a record only from its front side, so its end point must lie behind the plane). They are compact
+	// copies appended to flatPolys at [shadowFirst[l], shadowFirst[l] + shadowCount[l]); shadowCount[l] < 0 = no set, use all.
+	int shadowFirst[FRAY_SHADOW_LIGHTS], shadowCount[FRAY_SHADOW_LIGHTS];
+	int numFlatTotal;          // records in flatPolys including the shadow sets (what the kernels stage)
 };
 
 template <typename R> struct Ray {
@@ -722,7 +727,8 @@ FRAY_HD bool intersectNode(const DScene<R>& sc, int ni, const Ray<R>& ray, R max
 }
 
 // visible(), src/main.cpp:64-80
-template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const FlatTab& ft, const V3<R>& a, const V3<R>& b, RayCounters& cnt)
+// `light`: index of the light the end point b was sampled on (selects the light's shadow set), or -1
+template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const FlatTab& ft, const V3<R>& a, const V3<R>& b, int light, RayCounters& cnt)
 {
 	cnt.rays++;
 	cnt.shadow++;
@@ -732,7 +738,12 @@ template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const
 	const R maxDist = length(ray.dir);
 	ray.dir = normalized(ray.dir);
 	if constexpr ((F & FRAY_F_FLAT) != 0 && !Num<R>::kExact) {
-		if (flatAny(ft.polys, sc.numFlatGeom, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		int first = 0, count = sc.numFlatGeom;
+		if (light >= 0 && light < FRAY_SHADOW_LIGHTS && sc.shadowCount[light] >= 0) {
+			first = sc.shadowFirst[light];
+			count = sc.shadowCount[light];
+		}
+		if (flatAny(ft.polys + FRAY_FLAT_POLY_VEC * first, count, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 	}
 	if (F & FRAY_F_NODES) {
 		for (int n = 0; n < sc.numNodes; n++) {
@@ -984,7 +995,7 @@ FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShad
 			const float cosAngle = (float) dot(toLight, n);
 			float lambertTerm = (float) (cosAngle / distSqr);
 			lambertTerm = fmaxf(0.0f, lambertTerm);
-			if (visible<R, F>(sc, ft, shadowStart, lightPos, cnt)) {
+			if (visible<R, F>(sc, ft, shadowStart, lightPos, li, cnt)) {
 				Col c = diffuse * lightCol * lambertTerm;
 				if (s.type == FRAY_SHADER_PHONG) {
 					const V3<R> r = reflect(-toLight, n);
@@ -1244,7 +1255,7 @@ template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, const
 					brdfZero = false;
 				}
 				if (Num<R>::kExact || !brdfZero) {
-					const bool vis = visible<R, F>(sc, ft, h.ip + h.norm * eps, onLight, cnt);
+					const bool vis = visible<R, F>(sc, ft, h.ip + h.norm * eps, onLight, li, cnt);
 					if (vis && !brdfZero) {
 						const float probHit = (float) (1.0f / solidAngle);
 						const float probPick = 1.0f / (float) sc.numLights;

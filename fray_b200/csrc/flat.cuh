@@ -33,6 +33,8 @@ namespace fray {
 
 #define FRAY_FLAT_POLY_VEC 5   // float4 per record
 #define FRAY_MAX_FLAT 96       // records staged per scene (7.5 KB of shared memory + 4.5 KB of FlatInfo)
+#define FRAY_SHADOW_LIGHTS 8    // lights that get their own shadow set (core.cuh, DScene::shadowFirst)
+#define FRAY_MAX_SHADOW 160    // records in all shadow sets together (12.5 KB of shared memory)
 
 enum {
 	FRAY_FLAT_LIGHT = 1, // node = light index

@@ -62,9 +62,9 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 	extern __shared__ float4 flatSmem[];
 	FlatTab ft;
 	ft.polys = flatSmem;
-	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatAll);
+	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatTotal);
 	if (F & FRAY_F_FLAT) {
-		const int nPoly = FRAY_FLAT_POLY_VEC * sc.numFlatAll, nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * sc.numFlatAll;
+		const int nPoly = FRAY_FLAT_POLY_VEC * sc.numFlatTotal, nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * sc.numFlatAll;
 		const float4* gi = reinterpret_cast<const float4*>(sc.flatInfo);
 		for (int i = threadIdx.x; i < nPoly; i += blockDim.x) flatSmem[i] = sc.flatPolys[i];
 		for (int i = threadIdx.x; i < nInfo; i += blockDim.x) flatSmem[nPoly + i] = gi[i];
@@ -255,7 +255,7 @@ struct LaunchConfig {
 
 template <typename R> inline size_t flatSmemBytes(const DScene<R>& sc)
 {
-	return (size_t) sc.numFlatAll * (FRAY_FLAT_POLY_VEC * sizeof(float4) + sizeof(FlatInfo));
+	return (size_t) sc.numFlatTotal * FRAY_FLAT_POLY_VEC * sizeof(float4) + (size_t) sc.numFlatAll * sizeof(FlatInfo);
 }
 
 // one launch of the render (or AOV) kernel for precision R; defined in render_fp32.cu / render_fp64.cu

@@ -11,6 +11,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -257,6 +259,46 @@ template <typename R> struct SceneImage {
 		}
 		offsets.numFlatAll = (int) flatInfo.size();
 		offsets.lightsInFlat = 1;
+		// shadow sets (DScene::shadowFirst): a record can stop a ray towards light l only if some point of the light lies behind
+		// its plane. For the light sources of a room nearly every wall fails that test.
+		for (int l = 0; l < FRAY_SHADOW_LIGHTS; l++) { offsets.shadowFirst[l] = 0; offsets.shadowCount[l] = -1; }
+		int shadowRoom = FRAY_MAX_SHADOW;
+		for (int li = 0; li < s.num_lights && li < FRAY_SHADOW_LIGHTS; li++) {
+			const FrayGpuLight& l = s.lights[li];
+			std::vector<D3> pts;
+			if (l.type == FRAY_LIGHT_RECT) {
+				const D3 off{ l.T.offset[0], l.T.offset[1], l.T.offset[2] };
+				for (int k = 0; k < 4; k++) {
+					const D3 q = rowMul(D3{ (k & 1) ? 0.5 : -0.5, 0, (k & 2) ? 0.5 : -0.5 }, l.T.m);
+					pts.push_back(D3{ q.x + off.x, q.y + off.y, q.z + off.z });
+				}
+			} else {
+				pts.push_back(D3{ l.pos[0], l.pos[1], l.pos[2] });
+			}
+			std::vector<int> keep;
+			for (int r = 0; r < offsets.numFlatGeom; r++) {
+				const float4& pl = flatPolys[(size_t) FRAY_FLAT_POLY_VEC * r];
+				double behind = 1e300, scale = fabs((double) pl.w) + 1;
+				for (const D3& q: pts) {
+					behind = std::min(behind, pl.x * q.x + pl.y * q.y + pl.z * q.z - pl.w);
+					scale = std::max(scale, std::max(fabs(q.x), std::max(fabs(q.y), fabs(q.z))));
+				}
+				if (behind < 1e-4 * scale) keep.push_back(r); // the whole light is clearly in front otherwise
+			}
+			if ((int) keep.size() == offsets.numFlatGeom || (int) keep.size() > shadowRoom) continue; // nothing gained / no room
+			shadowRoom -= (int) keep.size();
+			offsets.shadowFirst[li] = (int) (flatPolys.size() / FRAY_FLAT_POLY_VEC);
+			offsets.shadowCount[li] = (int) keep.size();
+			for (int r: keep)
+				for (int k = 0; k < FRAY_FLAT_POLY_VEC; k++) flatPolys.push_back(flatPolys[(size_t) FRAY_FLAT_POLY_VEC * r + k]);
+		}
+		offsets.numFlatTotal = (int) (flatPolys.size() / FRAY_FLAT_POLY_VEC);
+		if (getenv("FRAY_GPU_VERBOSE")) {
+			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records", offsets.numFlatGeom, offsets.numFlatAll - offsets.numFlatGeom);
+			for (int l = 0; l < s.num_lights && l < FRAY_SHADOW_LIGHTS; l++)
+				if (offsets.shadowCount[l] >= 0) fprintf(stderr, ", shadow set of light %d: %d", l, offsets.shadowCount[l]);
+			fprintf(stderr, "\n");
+		}
 		return feat;
 	}
 
