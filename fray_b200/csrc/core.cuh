@@ -953,9 +953,11 @@ FRAY_HD void lightSample(const DLight<R>& l, Rng& rng, int sampleIdx, const V3<R
 		color = loadCol(l.color) * l.power;
 		return;
 	}
-	const int column = sampleIdx % l.xSubd;
-	const int row = sampleIdx / l.xSubd;
 	const R sx = (R) 1 / l.xSubd, sy = (R) 1 / l.ySubd;
+	int row;
+	if (Num<R>::kExact) row = sampleIdx / l.xSubd;
+	else row = (int) (((float) sampleIdx + 0.5f) * (float) sx); // exact for the small integers involved, no integer division
+	const int column = sampleIdx - row * l.xSubd;
 	const R px = column * sx + sx * (R) rng.randfloat();
 	const R py = row * sy + sy * (R) rng.randfloat();
 	if (wantColor) {
