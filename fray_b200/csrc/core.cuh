@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
+#include <string.h>
 
 #include "rng.cuh"
 #include "flat.cuh"
@@ -236,6 +237,9 @@ template <typename R> struct DScene {
 	const R* kdBox;     // 6 R per kd node: vmin xyz, vmax xyz
 	const int* leafRefs; // triangle indices relative to mesh.firstTri
 	const float* texels;
+	// fast precision only: one 48-byte record per triangle for the KD leaves (intersectMeshFast): plane (N, N.A) with
+	// N = AB ^ AC normalised, and the two barycentric planes lambda2(p) = e2.(p,1), lambda3(p) = e3.(p,1)
+	const float4* kdTris;
 	// fast precision only (flat.cuh): world-space convex polygons of the brute-force meshes and the rectangular lights
 	const float4* flatPolys;   // FRAY_FLAT_POLY_VEC float4 per polygon
 	const FlatInfo* flatInfo;  // one per polygon
@@ -566,6 +570,123 @@ FRAY_HD_HOT bool intersectMesh(const DScene<R>& sc, int meshIdx, const Ray<R>& r
 	return true;
 }
 
+
+// ---- fast-precision mesh traversal ------------------------------------------------------------------------------------
+// Same hits as Mesh::intersect / intersectKD (src/mesh.cpp:144-165, 357-394) up to ties, organised for the GPU:
+//   * the classic front-to-back KD walk over ray-parameter intervals: one 16-byte node fetch (LDG.128), one multiply and
+//     two compares per inner node, instead of the reference's two full box tests per inner node; the far child goes on a
+//     stack with its interval. The near child is the one on the origin's side of the split (src/mesh.cpp:368), a leaf hit
+//     ends the walk if it lies within the leaf's interval (the reference: within the leaf's box, src/mesh.cpp:384-391),
+//     otherwise the walk goes on with the tightened distance, exactly like info.dist does there;
+//   * triangles as 48-byte plane + barycentric-plane records (three LDG.128 per test, no division until the plane hit).
+template <bool ANYHIT>
+FRAY_HD_HOT bool intersectMeshFast(const DScene<float>& sc, int meshIdx, const Ray<float>& ray, float maxT, Hit<float>& h)
+{
+	const DMesh<float>& m = sc.meshes[meshIdx];
+	const float ox = ray.start.x, oy = ray.start.y, oz = ray.start.z, dx = ray.dir.x, dy = ray.dir.y, dz = ray.dir.z;
+	// RRay::prepareForTracing, src/bbox.h:49-54
+	const float rx = fabsf(dx) > 1e-12f ? 1.0f / dx : 1e12f, ry = fabsf(dy) > 1e-12f ? 1.0f / dy : 1e12f, rz = fabsf(dz) > 1e-12f ? 1.0f / dz : 1e12f;
+	// root box as three slabs (BBox::testIntersect, src/bbox.h:87-134, with its +-1e-6 slack scaled to FP32)
+	const float slack = Num<float>::slackEps(fmaxf(maxAbs(load3(m.bmin)), maxAbs(load3(m.bmax))));
+	float tmin, tmax;
+	{
+		const float ax0 = (m.bmin[0] - slack - ox) * rx, ax1 = (m.bmax[0] + slack - ox) * rx;
+		const float ay0 = (m.bmin[1] - slack - oy) * ry, ay1 = (m.bmax[1] + slack - oy) * ry;
+		const float az0 = (m.bmin[2] - slack - oz) * rz, az1 = (m.bmax[2] + slack - oz) * rz;
+		tmin = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+		tmax = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), maxT));
+		if (!(tmin <= tmax)) return false;
+	}
+	const bool cull = (m.flags & FRAY_MESH_BACKFACE_CULL) != 0;
+	float best = maxT;
+	int bestTri = -1;
+	float bestL2 = 0, bestL3 = 0;
+
+	// one triangle: plane hit, then the two barycentric planes (Triangle::intersectFast, src/triangle.cpp:66-94)
+	auto testTriangle = [&](int t) {
+		const float4 pl = sc.kdTris[3 * (size_t) t], e2 = sc.kdTris[3 * (size_t) t + 1], e3 = sc.kdTris[3 * (size_t) t + 2];
+		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, pl.z * dz));
+		if (cull && s > 0.0f) return; // dot(dir, gnormal) > 0, src/mesh.cpp:106
+		const float hh = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
+		const float tt = flatDivide(hh, s);
+		if (!(tt >= 0.0f && tt <= best)) return; // also rejects the parallel case (inf / NaN); `<=`: a later triangle wins ties
+		const float px = fmaf(dx, tt, ox), py = fmaf(dy, tt, oy), pz = fmaf(dz, tt, oz);
+		const float l2 = fmaf(e2.x, px, fmaf(e2.y, py, fmaf(e2.z, pz, e2.w)));
+		const float l3 = fmaf(e3.x, px, fmaf(e3.y, py, fmaf(e3.z, pz, e3.w)));
+		if (l2 < 0.0f || l3 < 0.0f || l2 + l3 > 1.0f) return;
+		best = tt;
+		bestTri = t;
+		bestL2 = l2;
+		bestL3 = l3;
+	};
+
+	bool found = false;
+	if (m.kdRoot < 0) {
+		for (int t = m.firstTri; t < m.firstTri + m.numTris; t++) {
+			testTriangle(t);
+			if (ANYHIT && bestTri >= 0) break;
+		}
+		found = bestTri >= 0;
+	} else {
+		int stackNode[FRAY_KD_STACK];
+		float stackTmin[FRAY_KD_STACK], stackTmax[FRAY_KD_STACK];
+		int sp = 0;
+		int ni = m.kdRoot;
+		const int4* nodes = reinterpret_cast<const int4*>(sc.kd);
+		for (;;) {
+			int4 n = nodes[ni];
+			while (n.x != 3) { // inner node: axis n.x, children n.y / n.y + 1, split position in n.w
+#if defined(__CUDA_ARCH__)
+				const float split = __int_as_float(n.w);
+#else
+				float split;
+				memcpy(&split, &n.w, sizeof(split));
+#endif
+				const float o = n.x == 0 ? ox : (n.x == 1 ? oy : oz), r = n.x == 0 ? rx : (n.x == 1 ? ry : rz);
+				const float ts = (split - o) * r;
+				// near child = the origin's side (src/mesh.cpp:368); an origin exactly on the split belongs to the side it moves into
+				const bool lowFirst = o < split || (o == split && r <= 0.0f);
+				const int nearChild = n.y + (lowFirst ? 0 : 1), farChild = n.y + (lowFirst ? 1 : 0);
+				if (ts > tmax || ts <= 0.0f) {
+					ni = nearChild; // the far side lies beyond the interval, or behind the origin
+				} else if (ts < tmin) {
+					ni = farChild;
+				} else {
+					if (sp < FRAY_KD_STACK) { stackNode[sp] = farChild; stackTmin[sp] = ts; stackTmax[sp] = tmax; sp++; }
+					ni = nearChild;
+					tmax = ts;
+				}
+				n = nodes[ni];
+			}
+			// leaf: n.y = first leaf reference, n.z = count
+			for (int i = 0; i < n.z; i++) testTriangle(m.firstTri + sc.leafRefs[n.y + i]);
+			if (bestTri >= 0) {
+				if (ANYHIT) { found = true; break; }
+				// a hit inside this leaf's interval is the closest one: everything still on the stack starts farther away
+				if (best <= tmax + slack + 1e-6f * tmax) { found = true; break; }
+			}
+			// next pending subtree that can still contain something closer
+			bool more = false;
+			while (sp > 0) {
+				sp--;
+				if (stackTmin[sp] <= best) { ni = stackNode[sp]; tmin = stackTmin[sp]; tmax = stackTmax[sp]; more = true; break; }
+			}
+			if (!more) break;
+		}
+		// a hit that no leaf interval confirmed is still a hit of a triangle of this mesh: unlike the reference's leaf-box
+		// rule there is nothing beyond the last interval, so it stands
+		if (!found && bestTri >= 0) found = true;
+	}
+	if (!found) return false;
+	h.dist = best;
+	h.ip = ray.start + ray.dir * best;
+	h.mesh = meshIdx;
+	h.tri = bestTri;
+	h.l2 = bestL2;
+	h.l3 = bestL3;
+	return true;
+}
+
 // geometry dispatch without CSG (the leaves of a CSG tree and plain nodes)
 template <typename R, bool ANYHIT>
 FRAY_HD bool intersectLeafGeom(const DScene<R>& sc, int gi, const Ray<R>& ray, R maxT, Hit<R>& h, bool needUV, bool needAttr)
@@ -577,7 +698,8 @@ FRAY_HD bool intersectLeafGeom(const DScene<R>& sc, int gi, const Ray<R>& ray, R
 		case FRAY_GEOM_SPHERE: ok = intersectSphere(g, ray, h, needUV); break;
 		case FRAY_GEOM_CUBE: ok = intersectCube(g, ray, h); break;
 		case FRAY_GEOM_MESH:
-			ok = intersectMesh<R, ANYHIT>(sc, g.mesh, ray, maxT, h);
+			if constexpr (Num<R>::kExact) ok = intersectMesh<R, ANYHIT>(sc, g.mesh, ray, maxT, h);
+			else ok = intersectMeshFast<ANYHIT>(sc, g.mesh, ray, maxT, h);
 			if (ok && needAttr) triangleAttributes(sc, g.mesh, h.tri, h.l2, h.l3, h.norm, h.u, h.v);
 			break;
 		default: ok = false; break;

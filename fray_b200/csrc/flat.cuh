@@ -27,6 +27,7 @@
 
 #if !defined(__CUDACC__)
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
 #endif
 
 namespace fray {

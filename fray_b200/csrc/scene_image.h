@@ -511,6 +511,29 @@ template <typename R> struct SceneImage {
 		for (size_t i = 0; i < normals.size(); i++) normals[i] = (R) s.normals[i];
 		for (size_t i = 0; i < uvs.size(); i++) uvs[i] = (R) s.uvs[i];
 		std::vector<float> texels(s.texels, s.texels + 3 * (size_t) s.num_texels);
+		// fast precision: plane + barycentric-plane records for the KD leaves (core.cuh, intersectMeshFast)
+		std::vector<float4> kdTris;
+		if (!Num<R>::kExact) {
+			kdTris.resize(3 * T);
+			for (int mi = 0; mi < s.num_meshes; mi++) {
+				const FrayGpuMesh& m = s.meshes[mi];
+				for (int t = 0; t < m.num_triangles; t++) {
+					const size_t ti = (size_t) m.first_triangle + t;
+					const double* a = s.vertices + 3 * ((size_t) m.first_vertex + s.tri_v[3 * ti]);
+					const D3 A{ a[0], a[1], a[2] };
+					const D3 AB{ s.tri_ab[3 * ti], s.tri_ab[3 * ti + 1], s.tri_ab[3 * ti + 2] }, AC{ s.tri_ac[3 * ti], s.tri_ac[3 * ti + 1], s.tri_ac[3 * ti + 2] };
+					const D3 N{ s.tri_abxac[3 * ti], s.tri_abxac[3 * ti + 1], s.tri_abxac[3 * ti + 2] };
+					const double nn = dt(N, N);
+					float4 zero = plane4(D3{ 0, 0, 0 }, 0);
+					if (!(nn > 0)) { kdTris[3 * ti] = kdTris[3 * ti + 1] = kdTris[3 * ti + 2] = zero; continue; }
+					const D3 Nu = scl(N, 1 / sqrt(nn));
+					const D3 m2 = scl(crs(AC, N), 1 / nn), m3 = scl(crs(N, AB), 1 / nn);
+					kdTris[3 * ti] = plane4(Nu, dt(Nu, A));
+					kdTris[3 * ti + 1] = plane4(m2, -dt(m2, A));
+					kdTris[3 * ti + 2] = plane4(m3, -dt(m3, A));
+				}
+			}
+		}
 
 #define FRAY_PUT(member, vec) d.member = reinterpret_cast<decltype(d.member)>(append(vec))
 		FRAY_PUT(nodes, nodes);
@@ -536,6 +559,7 @@ template <typename R> struct SceneImage {
 		FRAY_PUT(kdBox, kdBox);
 		FRAY_PUT(leafRefs, leafRefs);
 		FRAY_PUT(texels, texels);
+		FRAY_PUT(kdTris, kdTris);
 		FRAY_PUT(flatPolys, flatPolys);
 		FRAY_PUT(flatInfo, flatInfo);
 #undef FRAY_PUT
@@ -553,7 +577,7 @@ template <typename R> struct SceneImage {
 		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
 		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
 		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
-		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo);
+		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris);
 #undef FRAY_REBASE
 		return d;
 	}
