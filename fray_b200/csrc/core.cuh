@@ -929,9 +929,15 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 				if ((fi.flags & FRAY_FLAT_QUAD) && fi.diag.x * best.ip.x + fi.diag.y * best.ip.y + fi.diag.z * best.ip.z + fi.diag.w < 0) best.tri = fi.tri1;
 				if ((F & FRAY_F_ATTR) && (fi.flags & FRAY_FLAT_ATTR)) {
 					const DNode<R>& nd = sc.nodes[node];
-					flatBarycentrics(sc, nd, best.tri, best.ip, best.l2, best.l3);
-					triangleAttributes(sc, fi.mesh, best.tri, best.l2, best.l3, best.norm, best.u, best.v);
-					best.norm = xfDir(nd.T, best.norm);
+					if (fi.flags & FRAY_FLAT_PLANE) { // info.u = ip.x, info.v = ip.z in object space, src/geometry.cpp:45-46
+						const V3<R> q = xfUnpoint(nd.T, best.ip);
+						best.u = q.x;
+						best.v = q.z;
+					} else {
+						flatBarycentrics(sc, nd, best.tri, best.ip, best.l2, best.l3);
+						triangleAttributes(sc, fi.mesh, best.tri, best.l2, best.l3, best.norm, best.u, best.v);
+						best.norm = xfDir(nd.T, best.norm);
+					}
 				}
 			}
 		}

@@ -12,6 +12,7 @@
 //     ray transform and no box test remain (a triangle hit implies the box hit);
 //   * two fan triangles of one OBJ face that are coplanar and form a convex quadrilateral are merged into one record
 //     (the union of the two acceptance regions is the quadrilateral), halving the work for quad meshes;
+//   * every Plane primitive (src/geometry.cpp:30-50) as the world-space image of its bounded square, one record per side;
 //   * every RectLight as the world-space image of its unit square, facing the way src/lights.cpp:85-86 demands.
 // A record is a plane plus up to four inward edge planes (80 bytes, five float4):
 //     plane = (N, dN)          t = (dN - N.o) / (N.d)   hit point p = o + t d   front side: N.d < 0 (back-face culling,
@@ -40,7 +41,8 @@ namespace fray {
 enum {
 	FRAY_FLAT_LIGHT = 1, // node = light index
 	FRAY_FLAT_ATTR = 2,  // the mesh interpolates normals and/or uvs: barycentrics are recomputed for the winner
-	FRAY_FLAT_QUAD = 4   // two triangles merged; `diag` tells them apart
+	FRAY_FLAT_QUAD = 4,  // two triangles merged; `diag` tells them apart
+	FRAY_FLAT_PLANE = 8  // a Plane primitive: with FRAY_FLAT_ATTR, (u, v) = object-space (x, z) of the hit
 };
 
 struct FlatInfo {

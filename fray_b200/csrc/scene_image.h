@@ -139,6 +139,42 @@ template <typename R> struct SceneImage {
 		for (int ni = 0; ni < s.num_nodes; ni++) {
 			const FrayGpuNode& n = s.nodes[ni];
 			const FrayGpuGeometry& g = s.geometries[n.geometry];
+			if (g.type == FRAY_GEOM_PLANE) {
+				// Plane::intersect, src/geometry.cpp:30-50: the square |x|, |z| <= limit of the object-space plane y = height, hit
+				// from either side, normal always +y. Under the node transform that is a world-space parallelogram: two records.
+				if (room < 2) continue;
+				const double height = g.p[0], limit = g.p[1];
+				const double* I = n.T.inv;
+				const D3 off{ n.T.offset[0], n.T.offset[1], n.T.offset[2] };
+				const D3 cx{ I[0], I[3], I[6] }, cy{ I[1], I[4], I[7] }, cz{ I[2], I[5], I[8] }; // object x(p) = (p - off) . cx, ...
+				const double ly = sqrt(dt(cy, cy));
+				if (!(ly > 0) || !(limit > 0)) continue;
+				float4 rec[5];
+				const D3 Nu = scl(cy, 1 / ly);
+				rec[0] = plane4(Nu, (height + dt(off, cy)) / ly);
+				if (limit < 1e30) {
+					rec[1] = plane4(scl(cx, -1 / limit), 1 + dt(off, cx) / limit);
+					rec[2] = plane4(scl(cx, 1 / limit), 1 - dt(off, cx) / limit);
+					rec[3] = plane4(scl(cz, -1 / limit), 1 + dt(off, cz) / limit);
+					rec[4] = plane4(scl(cz, 1 / limit), 1 - dt(off, cz) / limit);
+				} else {
+					rec[1] = rec[2] = rec[3] = rec[4] = always;
+				}
+				FlatInfo fi;
+				memset(&fi, 0, sizeof(fi));
+				D3 w{ n.T.m[3], n.T.m[4], n.T.m[5] }; // (0, 1, 0) * m, normalised (src/geometry.cpp:204, src/matrix.cpp:153-156)
+				const double lw = sqrt(dt(w, w));
+				if (lw > 0) w = scl(w, 1 / lw);
+				fi.nx = (float) w.x; fi.ny = (float) w.y; fi.nz = (float) w.z;
+				const bool attr = nodes[ni].needsUV || n.bump >= 0;
+				fi.node = ni; fi.tri0 = fi.tri1 = -1; fi.mesh = -1; fi.flags = attr ? (FRAY_FLAT_ATTR | FRAY_FLAT_PLANE) : 0;
+				pushFlat(rec, fi, true);
+				room -= 2;
+				nodes[ni].inFlat = 1;
+				feat |= FRAY_F_FLAT;
+				if (attr) feat |= FRAY_F_ATTR;
+				continue;
+			}
 			if (g.type != FRAY_GEOM_MESH) continue;
 			const FrayGpuMesh& m = s.meshes[g.mesh];
 			if (m.kd_root >= 0 || m.num_triangles <= 0) continue;
