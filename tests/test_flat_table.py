@@ -1,0 +1,61 @@
+"""The flat polygon table of the fast-precision path (fray_b200/csrc/flat.cuh, built by scene_image.h) on a scene that
+exercises what the bundled scenes do not: rotated, non-uniformly scaled and mirrored nodes over brute-force meshes, a two-sided
+mesh, transformed planes (one textured: object-space uv), a point light beside a rectangular light (per-light shadow sets).
+The CPU half runs the very same device code compiled for the host (tests/emul); the GPU half goes through the C ABI."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import fray_b200 as fb
+import oracle_util as ou
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def scene(data_dir):
+    dst = os.path.join(data_dir, "flat_transforms__test.fray")
+    shutil.copyfile(os.path.join(HERE, "scenes", "flat_transforms.fray"), dst)
+    return fb.Scene(dst)
+
+
+def check(scene, render):
+    want, ostats = ou.oracle_render(scene, seed=7)
+    waov, _ = ou.oracle_render(scene, mode=fb.RENDER_AOV)
+    # the scene really contains what it is meant to test
+    nodes = set(np.unique(waov[..., 0]).astype(int))
+    assert {0, 1, 2, 3, 4, 5} <= nodes, nodes
+    got, stats = render(scene, fb.FP32, seed=7)
+    frac, rmse, mx = ou.compare(want, got, 1e-3)
+    assert frac >= 0.995 and rmse < 5e-3, (frac, rmse, mx)
+    assert abs(stats.rays - ostats.rays) <= 0.002 * ostats.rays
+    gaov, _ = render(scene, fb.FP32, mode=fb.RENDER_AOV)
+    assert (gaov[..., 0] == waov[..., 0]).mean() >= 0.998
+    hit = (waov[..., 0] >= 0) & (gaov[..., 0] == waov[..., 0])
+    np.testing.assert_allclose(gaov[..., 2][hit], waov[..., 2][hit], rtol=2e-4)
+    return got
+
+
+def test_flat_table_on_the_host_emulator(scene):
+    from test_emul_vs_oracle import emul as emul_fixture
+    render = emul_fixture.__wrapped__()
+    check(scene, render)
+    # parity precision never uses the table and must agree with the oracle exactly as everywhere else
+    want, ostats = ou.oracle_render(scene, seed=7)
+    got, stats = render(scene, fb.FP64, seed=7)
+    assert ou.compare(want, got, 1e-5)[0] == 1.0 and stats.rays == ostats.rays
+
+
+@pytest.mark.gpu
+def test_flat_table_on_the_gpu(scene):
+    def render(sc, precision, **kw):
+        ctx = fb.GpuContext(sc, 0, precision)
+        out = ctx.render(**kw)
+        ctx.close()
+        return out
+    check(scene, render)
+    want, ostats = ou.oracle_render(scene, seed=7)
+    got, stats = render(scene, fb.FP64, seed=7)
+    assert ou.compare(want, got, 2e-5)[0] == 1.0 and stats.rays == ostats.rays
