@@ -251,6 +251,7 @@ template <typename R> struct DScene {
 	// copies appended to flatPolys at [shadowFirst[l], shadowFirst[l] + shadowCount[l]); shadowCount[l] < 0 = no set, use all.
 	int shadowFirst[FRAY_SHADOW_LIGHTS], shadowCount[FRAY_SHADOW_LIGHTS];
 	int numFlatTotal;          // records in flatPolys including the shadow sets (what the kernels stage)
+	int numFlatSpheres;        // (centre, R^2) vectors that follow the records in flatPolys; their FlatInfo follow the lights'
 };
 
 template <typename R> struct Ray {
@@ -785,18 +786,20 @@ template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
 #define FRAY_F_TEX 4    // textures, bump maps or an environment exist
 #define FRAY_F_FLAT 8   // fast precision: the flat polygon table (flat.cuh) holds the brute-force meshes and the lights
 #define FRAY_F_ATTR 16  // some flat record interpolates normals / uvs
+#define FRAY_F_SPHERES 32 // the flat table has a sphere list
 #define FRAY_F_GENERIC (FRAY_F_NODES | FRAY_F_TEX)
 
 // The kernel variants compiled per precision, smallest first; a scene runs on the first one that covers its feature bits.
 template <typename R> struct Variants;
 template <> struct Variants<float> {
-	static constexpr int count = 4;
+	static constexpr int count = 5;
 	static constexpr int mask(int i)
 	{
-		return i == 0 ? FRAY_F_FLAT                                              // brute-force meshes + lights only (cornell_box)
-		     : i == 1 ? (FRAY_F_FLAT | FRAY_F_NODES)                               // + analytic primitives / KD meshes, untextured (smallpt)
-		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX)    // everything but CSG
-		              : (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
+		return i == 0 ? FRAY_F_FLAT                                                      // brute-force meshes, planes, lights (cornell_box)
+		     : i == 1 ? (FRAY_F_FLAT | FRAY_F_SPHERES)                                     // + translated spheres (smallpt)
+		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
+		     : i == 3 ? (FRAY_F_FLAT | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX) // everything but CSG
+		              : (FRAY_F_FLAT | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
 	}
 };
 template <> struct Variants<double> {
@@ -808,6 +811,7 @@ template <> struct Variants<double> {
 struct FlatTab {
 	const float4* polys;
 	const FlatInfo* info;
+	const float4* spheres;
 };
 
 // Node::intersect, src/geometry.cpp:196-208. On success h is in WORLD space (ip, norm, dist).
@@ -866,6 +870,7 @@ template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const
 			count = sc.shadowCount[light];
 		}
 		if (flatAny(ft.polys + FRAY_FLAT_POLY_VEC * first, count, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		if ((F & FRAY_F_SPHERES) && flatSpheresAny(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 	}
 	if (F & FRAY_F_NODES) {
 		for (int n = 0; n < sc.numNodes; n++) {
@@ -915,6 +920,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 	if constexpr ((F & FRAY_F_FLAT) != 0 && !Num<R>::kExact) {
 		int idx = -1;
 		flatClosest(ft.polys, sc.numFlatAll, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
+		if (F & FRAY_F_SPHERES) flatSpheresClosest(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx, sc.numFlatAll);
 		if (idx >= 0) {
 			const FlatInfo& fi = ft.info[idx];
 			if (fi.flags & FRAY_FLAT_LIGHT) {
@@ -927,9 +933,16 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 				best.mesh = fi.mesh;
 				best.tri = fi.tri0;
 				if ((fi.flags & FRAY_FLAT_QUAD) && fi.diag.x * best.ip.x + fi.diag.y * best.ip.y + fi.diag.z * best.ip.z + fi.diag.w < 0) best.tri = fi.tri1;
+				if ((F & FRAY_F_SPHERES) && (fi.flags & FRAY_FLAT_SPHERE)) { // info.norm = ip - O, normalised (src/geometry.cpp:71-72)
+					const float4 sp = ft.spheres[idx - sc.numFlatAll];
+					best.norm = normalized(best.ip - V3<R>(sp.x, sp.y, sp.z));
+				}
 				if ((F & FRAY_F_ATTR) && (fi.flags & FRAY_FLAT_ATTR)) {
 					const DNode<R>& nd = sc.nodes[node];
-					if (fi.flags & FRAY_FLAT_PLANE) { // info.u = ip.x, info.v = ip.z in object space, src/geometry.cpp:45-46
+					if (fi.flags & FRAY_FLAT_SPHERE) { // spherical coordinates of the normal, src/geometry.cpp:73-80
+						best.u = (R) ((atan2(best.norm.z, best.norm.x) / (R) FRAY_PI * 180 + 180) / 360);
+						best.v = (R) (1 - (asin(best.norm.y) / (R) FRAY_PI * 180 + 90) / 180);
+					} else if (fi.flags & FRAY_FLAT_PLANE) { // info.u = ip.x, info.v = ip.z in object space, src/geometry.cpp:45-46
 						const V3<R> q = xfUnpoint(nd.T, best.ip);
 						best.u = q.x;
 						best.v = q.z;

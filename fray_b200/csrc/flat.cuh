@@ -42,7 +42,8 @@ enum {
 	FRAY_FLAT_LIGHT = 1, // node = light index
 	FRAY_FLAT_ATTR = 2,  // the mesh interpolates normals and/or uvs: barycentrics are recomputed for the winner
 	FRAY_FLAT_QUAD = 4,  // two triangles merged; `diag` tells them apart
-	FRAY_FLAT_PLANE = 8  // a Plane primitive: with FRAY_FLAT_ATTR, (u, v) = object-space (x, z) of the hit
+	FRAY_FLAT_PLANE = 8, // a Plane primitive: with FRAY_FLAT_ATTR, (u, v) = object-space (x, z) of the hit
+	FRAY_FLAT_SPHERE = 16 // a Sphere primitive under a pure translation: record = (centre, R^2) in the sphere list
 };
 
 struct FlatInfo {
@@ -108,6 +109,46 @@ FRAY_HD bool flatAny(const float4* __restrict__ P, int n, float ox, float oy, fl
 	for (int i = 0; i < n; i++) {
 		float t;
 		hit |= (flatTest(P + FRAY_FLAT_POLY_VEC * i, ox, oy, oz, dx, dy, dz, t) >= 0.0f) & (t < tMax);
+	}
+	return hit;
+}
+
+// ---- spheres ---------------------------------------------------------------------------------------------------------
+// Sphere::intersect (src/geometry.cpp:52-83) for sphere nodes whose transform is a pure translation, as world-space
+// (centre, R^2) records walked like the polygon records. Nearest non-negative root, the far one from inside; evaluated in the
+// cancellation-free form the fast path uses everywhere (core.cuh, intersectSphere): discriminant from the perpendicular
+// offset, roots as q and c / q.
+FRAY_HD bool flatSphereTest(const float4 sp, float ox, float oy, float oz, float dx, float dy, float dz, float& t)
+{
+	const float hx = ox - sp.x, hy = oy - sp.y, hz = oz - sp.z;
+	const float b = -(dx * hx + dy * hy + dz * hz);
+	const float qx = fmaf(dx, b, hx), qy = fmaf(dy, b, hy), qz = fmaf(dz, b, hz);
+	const float disc = sp.w - (qx * qx + qy * qy + qz * qz);
+	const float c = (hx * hx + hy * hy + hz * hz) - sp.w;
+	const float sq = sqrtf(fmaxf(disc, 0.0f));
+	const float q = b + (b < 0.0f ? -sq : sq);
+	const float p1 = q, p2 = (q != 0.0f) ? c / q : 0.0f;
+	const float smaller = fminf(p1, p2), larger = fmaxf(p1, p2);
+	t = (smaller >= 0.0f) ? smaller : larger;
+	return (disc >= 0.0f) & (larger >= 0.0f);
+}
+
+FRAY_HD void flatSpheresClosest(const float4* __restrict__ S, int n, float ox, float oy, float oz, float dx, float dy, float dz, float& tBest, int& idx, int idxBase)
+{
+	for (int i = 0; i < n; i++) {
+		float t;
+		const bool ok = flatSphereTest(S[i], ox, oy, oz, dx, dy, dz, t) & (t < tBest);
+		tBest = ok ? t : tBest;
+		idx = ok ? idxBase + i : idx;
+	}
+}
+
+FRAY_HD bool flatSpheresAny(const float4* __restrict__ S, int n, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
+{
+	bool hit = false;
+	for (int i = 0; i < n; i++) {
+		float t;
+		hit |= flatSphereTest(S[i], ox, oy, oz, dx, dy, dz, t) & (t < tMax);
 	}
 	return hit;
 }

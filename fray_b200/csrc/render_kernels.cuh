@@ -61,13 +61,16 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 {
 	extern __shared__ float4 flatSmem[];
 	FlatTab ft;
+	// layout: records (incl. shadow sets) | spheres | FlatInfo (records, lights, spheres)
+	const int nVec = FRAY_FLAT_POLY_VEC * sc.numFlatTotal + sc.numFlatSpheres;
 	ft.polys = flatSmem;
-	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatTotal);
+	ft.spheres = flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatTotal;
+	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + nVec);
 	if (F & FRAY_F_FLAT) {
-		const int nPoly = FRAY_FLAT_POLY_VEC * sc.numFlatTotal, nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * sc.numFlatAll;
+		const int nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * (sc.numFlatAll + sc.numFlatSpheres);
 		const float4* gi = reinterpret_cast<const float4*>(sc.flatInfo);
-		for (int i = threadIdx.x; i < nPoly; i += blockDim.x) flatSmem[i] = sc.flatPolys[i];
-		for (int i = threadIdx.x; i < nInfo; i += blockDim.x) flatSmem[nPoly + i] = gi[i];
+		for (int i = threadIdx.x; i < nVec; i += blockDim.x) flatSmem[i] = sc.flatPolys[i];
+		for (int i = threadIdx.x; i < nInfo; i += blockDim.x) flatSmem[nVec + i] = gi[i];
 		__syncthreads();
 	}
 	return ft;
@@ -255,7 +258,7 @@ struct LaunchConfig {
 
 template <typename R> inline size_t flatSmemBytes(const DScene<R>& sc)
 {
-	return (size_t) sc.numFlatTotal * FRAY_FLAT_POLY_VEC * sizeof(float4) + (size_t) sc.numFlatAll * sizeof(FlatInfo);
+	return ((size_t) sc.numFlatTotal * FRAY_FLAT_POLY_VEC + sc.numFlatSpheres) * sizeof(float4) + (size_t) (sc.numFlatAll + sc.numFlatSpheres) * sizeof(FlatInfo);
 }
 
 // one launch of the render (or AOV) kernel for precision R; defined in render_fp32.cu / render_fp64.cu

@@ -135,6 +135,8 @@ template <typename R> struct SceneImage {
 		for (int i = 0; i < s.num_lights; i++) numRect += s.lights[i].type == FRAY_LIGHT_RECT;
 		if (numRect > FRAY_MAX_FLAT / 2) return 0; // absurd: leave everything to the generic loops
 		int room = FRAY_MAX_FLAT - numRect;
+		std::vector<float4> spheres;
+		std::vector<FlatInfo> sphereInfo;
 
 		for (int ni = 0; ni < s.num_nodes; ni++) {
 			const FrayGpuNode& n = s.nodes[ni];
@@ -172,6 +174,26 @@ template <typename R> struct SceneImage {
 				room -= 2;
 				nodes[ni].inFlat = 1;
 				feat |= FRAY_F_FLAT;
+				if (attr) feat |= FRAY_F_ATTR;
+				continue;
+			}
+			if (g.type == FRAY_GEOM_SPHERE) {
+				// only under a pure translation: anything else turns the sphere into an ellipsoid (generic node loop)
+				bool pure = true;
+				for (int k = 0; k < 9; k++)
+					if (n.T.m[k] != ((k % 4 == 0) ? 1.0 : 0.0)) pure = false;
+				if (!pure || (int) spheres.size() >= 16) continue;
+				float4 sp;
+				sp.x = (float) (g.p[0] + n.T.offset[0]); sp.y = (float) (g.p[1] + n.T.offset[1]); sp.z = (float) (g.p[2] + n.T.offset[2]);
+				sp.w = (float) (g.p[3] * g.p[3]);
+				FlatInfo fi;
+				memset(&fi, 0, sizeof(fi));
+				const bool attr = nodes[ni].needsUV || n.bump >= 0;
+				fi.node = ni; fi.tri0 = fi.tri1 = -1; fi.mesh = -1; fi.flags = FRAY_FLAT_SPHERE | (attr ? FRAY_FLAT_ATTR : 0);
+				spheres.push_back(sp);
+				sphereInfo.push_back(fi);
+				nodes[ni].inFlat = 1;
+				feat |= FRAY_F_FLAT | FRAY_F_SPHERES;
 				if (attr) feat |= FRAY_F_ATTR;
 				continue;
 			}
@@ -329,8 +351,12 @@ template <typename R> struct SceneImage {
 				for (int k = 0; k < FRAY_FLAT_POLY_VEC; k++) flatPolys.push_back(flatPolys[(size_t) FRAY_FLAT_POLY_VEC * r + k]);
 		}
 		offsets.numFlatTotal = (int) (flatPolys.size() / FRAY_FLAT_POLY_VEC);
+		offsets.numFlatSpheres = (int) spheres.size();
+		flatPolys.insert(flatPolys.end(), spheres.begin(), spheres.end());
+		flatInfo.insert(flatInfo.end(), sphereInfo.begin(), sphereInfo.end());
 		if (getenv("FRAY_GPU_VERBOSE")) {
-			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records", offsets.numFlatGeom, offsets.numFlatAll - offsets.numFlatGeom);
+			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records, %d spheres", offsets.numFlatGeom, offsets.numFlatAll - offsets.numFlatGeom,
+			        offsets.numFlatSpheres);
 			for (int l = 0; l < s.num_lights && l < FRAY_SHADOW_LIGHTS; l++)
 				if (offsets.shadowCount[l] >= 0) fprintf(stderr, ", shadow set of light %d: %d", l, offsets.shadowCount[l]);
 			fprintf(stderr, "\n");

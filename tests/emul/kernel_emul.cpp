@@ -71,12 +71,14 @@ static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out
 	FlatTab ft;
 	ft.polys = sc.flatPolys;
 	ft.info = sc.flatInfo;
+	ft.spheres = sc.flatPolys + FRAY_FLAT_POLY_VEC * sc.numFlatTotal;
 	const int need = img.features;
 	auto run = [&]() { // the same variant selection as VariantDispatch in render_kernels.cuh
 		if (Variants<R>::count > 0 && (need & ~Variants<R>::mask(0)) == 0) renderRows<R, Variants<R>::mask(0)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 		else if (Variants<R>::count > 1 && (need & ~Variants<R>::mask(1)) == 0) renderRows<R, Variants<R>::mask(1)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 		else if (Variants<R>::count > 2 && (need & ~Variants<R>::mask(2)) == 0) renderRows<R, Variants<R>::mask(2)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
-		else renderRows<R, Variants<R>::mask(3)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else if (Variants<R>::count > 3 && (need & ~Variants<R>::mask(3)) == 0) renderRows<R, Variants<R>::mask(3)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else renderRows<R, Variants<R>::mask(4)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 	};
 	for (int t = 1; t < threads; t++) pool.emplace_back(run);
 	run();

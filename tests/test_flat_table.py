@@ -1,6 +1,7 @@
 """The flat polygon table of the fast-precision path (fray_b200/csrc/flat.cuh, built by scene_image.h) on a scene that
 exercises what the bundled scenes do not: rotated, non-uniformly scaled and mirrored nodes over brute-force meshes, a two-sided
-mesh, transformed planes (one textured: object-space uv), a point light beside a rectangular light (per-light shadow sets).
+mesh, transformed planes (one textured: object-space uv), a translated textured sphere (sphere list, spherical uv) next to a
+squashed one (node loop), a point light beside a rectangular light (per-light shadow sets).
 The CPU half runs the very same device code compiled for the host (tests/emul); the GPU half goes through the C ABI."""
 import os
 import shutil
@@ -26,7 +27,7 @@ def check(scene, render):
     waov, _ = ou.oracle_render(scene, mode=fb.RENDER_AOV)
     # the scene really contains what it is meant to test
     nodes = set(np.unique(waov[..., 0]).astype(int))
-    assert {0, 1, 2, 3, 4, 5} <= nodes, nodes
+    assert {0, 1, 2, 3, 4, 5, 6, 7} <= nodes, nodes
     got, stats = render(scene, fb.FP32, seed=7)
     frac, rmse, mx = ou.compare(want, got, 1e-3)
     assert frac >= 0.995 and rmse < 5e-3, (frac, rmse, mx)
