@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""Render one bundled scene a few times on cuda:0 and print the device time (a short command to put under ncu).
+
+    python tools/render_once.py hw9/dragon [--frames 3] [--fp64] [key=value ...]      e.g. pathsPerPixel=256 frameWidth=1920
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import fray_b200 as fb
+import oracle_util as ou
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    name = args[0]
+    settings = dict(a.split("=", 1) for a in args[1:])
+    frames = int(sys.argv[sys.argv.index("--frames") + 1]) if "--frames" in sys.argv else 3
+    precision = fb.FP64 if "--fp64" in sys.argv else fb.FP32
+    if name == "forest":
+        settings.setdefault("interactive", "off")
+    sc = fb.Scene(ou.override_scene(name, "once", settings or None))
+    ctx = fb.GpuContext(sc, 0, precision)
+    for _ in range(frames):
+        img, s = ctx.render()
+        print(f"{name} {sc.width}x{sc.height} spp {sc.spp}: {s.device_ms:.3f} ms, {s.rays} rays, {s.rays / s.device_ms / 1e3:.1f} Mrays/s, mean {img.mean():.5f}", flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
