@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -266,14 +267,15 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	memset(&p, 0, sizeof(p));
 	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
 	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
-	// chunk size: every lane of the grid should see >= ~32 items, so that the drain at the end of the kernel (lanes running
+	// chunk size: every lane of the grid should see >= ~20 items (measured optimum for a 1.5 ms call: 2 paths per item), so that the drain at the end of the kernel (lanes running
 	// dry while the last items finish; an item of C paths takes C x ~35 us on a busy SM) is a few percent of the call even
 	// when 8 GPUs share a frame; the scratch buffer (one RGB sum per pixel and chunk) is kept below 192 MB
 	const int samples = std::max(1, s1 - s0);
 	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) cfg.gridBlocks * 128.0);
-	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 32.0)));
+	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 20.0)));
 	const double maxChunks = std::max(1.0, 192e6 / ((double) ownedTiles * 32.0 * 12.0));
 	C = std::max(C, (int) ((samples + maxChunks - 1) / maxChunks));
+	if (const char* e = getenv("FRAY_GPU_CHUNK")) C = std::max(1, atoi(e)); // experiments only
 	C = std::min(C, samples);
 	p.chunk = C;
 	p.numChunks = (samples + C - 1) / C;
