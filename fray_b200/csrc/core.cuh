@@ -1174,16 +1174,26 @@ template <typename R> FRAY_HD void orthonormalSystem(const V3<R>& a, V3<R>& b, V
 	c = cross(a, b);
 }
 
-// one pending Whitted ray: radiance(ray) * weight is added to the pixel
+// One pending piece of the Whitted ray tree. FRAY_TASK_RAY: radiance(ray) * weight is added to the pixel.
+// FRAY_TASK_GLOSSY: the samples k..ns-1 of a glossy reflection (Reflection::shade, src/shading.cpp:176-200) that have not
+// been traced yet -- a generator: popping it produces sample k and puts the rest back, so that a hit with 25 glossy samples
+// occupies one stack entry instead of 25 (the per-thread stacks live in local memory; what they touch has to fit in L2).
+enum { FRAY_TASK_RAY = 0, FRAY_TASK_GLOSSY = 1 };
+
 template <typename R> struct RayTask {
-	V3<R> start, dir;
-	Col weight;
-	int depth;
-	uint32_t branch; // RNG stream of the raytrace() invocation this ray starts
-	uint32_t count;  // draws already consumed from that stream (glossy direction sampling)
+	V3<R> start, dir; // GLOSSY: dir = direction of the INCOMING ray
+	Col weight;       // GLOSSY: weight of one sample
+	int depth;        // GLOSSY: depth of the reflecting invocation (samples start at depth + 1)
+	uint32_t branch;  // RNG stream of the raytrace() invocation this ray starts; GLOSSY: stream of the reflecting invocation
+	uint32_t count;   // draws already consumed from that stream; GLOSSY: draws consumed when the reflection was spawned
+	int kind;
+	// GLOSSY only
+	V3<R> n;          // face-forwarded normal at the hit
+	int shader, k, ns;
+	uint32_t k0;      // child number of sample 0 within the reflecting invocation
 };
 
-#define FRAY_TASK_STACK 48
+#define FRAY_TASK_STACK 32
 
 template <typename R> struct WhittedState {
 	RayTask<R> stack[FRAY_TASK_STACK];
@@ -1209,6 +1219,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 			const uint32_t drawsAtSpawn = rng.count;
 			if (s.pureReflection) {
 				RayTask<R> t;
+				t.kind = FRAY_TASK_RAY;
 				t.start = start;
 				t.dir = reflect(rayDir, n);
 				t.weight = weight * loadCol(s.mult);
@@ -1218,36 +1229,22 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 				if (ws.sp < FRAY_TASK_STACK) ws.stack[ws.sp++] = t; else ws.overflow = 1;
 				return;
 			}
-			V3<R> b, c;
-			orthonormalSystem(n, b, c);
 			const int ns = depth == 0 ? s.numSamples : 3; // LOW_GLOSSY_SAMPLES, src/constants.h:36
-			const Col w = weight * loadCol(s.mult) / (float) ns;
-			// children are pushed in reverse so that sample 0 is traced first (order does not change the result)
-			const uint32_t k0 = spawn;
+			RayTask<R> t;
+			t.kind = FRAY_TASK_GLOSSY;
+			t.start = start;
+			t.dir = rayDir;
+			t.weight = weight * loadCol(s.mult) / (float) ns;
+			t.depth = depth;
+			t.branch = rng.branch;
+			t.count = drawsAtSpawn;
+			t.n = n;
+			t.shader = shaderIdx;
+			t.k = 0;
+			t.ns = ns;
+			t.k0 = spawn;
 			spawn += (uint32_t) ns;
-			for (int i = ns - 1; i >= 0; i--) {
-				Rng child;
-				child.init(rng.seed, rng.pixel, rng.sample, rngChildBranch(rng.branch, drawsAtSpawn, k0 + (uint32_t) i));
-				V3<R> reflected;
-				for (;;) {
-					// Random::unitDiscSample, src/random_generator.cpp:71-80
-					R sn, cs;
-					Num<R>::sincos2pi(Num<R>::draw(child), sn, cs);
-					const R rad = Num<R>::sqrtR(Num<R>::draw(child));
-					const R x = sn * rad * s.deflectionScaling, y = cs * rad * s.deflectionScaling;
-					const V3<R> nn = normalized(n + b * x + c * y);
-					reflected = reflect(rayDir, nn);
-					if (dot(reflected, n) > 0) break;
-				}
-				RayTask<R> t;
-				t.start = start;
-				t.dir = reflected;
-				t.weight = w;
-				t.depth = depth + 1;
-				t.branch = child.branch;
-				t.count = child.count;
-				if (ws.sp < FRAY_TASK_STACK) ws.stack[ws.sp++] = t; else ws.overflow = 1;
-			}
+			if (ns > 0) { if (ws.sp < FRAY_TASK_STACK) ws.stack[ws.sp++] = t; else ws.overflow = 1; }
 			return;
 		}
 		case FRAY_SHADER_REFR: {
@@ -1256,6 +1253,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 			V3<R> refracted;
 			if (!refractDir(rayDir, n, ior, refracted)) return; // total internal reflection: black
 			RayTask<R> t;
+			t.kind = FRAY_TASK_RAY;
 			t.start = h.ip - n * Num<R>::offsetEps(maxAbs(h.ip));
 			t.dir = refracted;
 			t.weight = weight * loadCol(s.mult);
@@ -1304,6 +1302,56 @@ FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R
 	if (F & FRAY_F_TEX) applyBump(sc, nd, h);
 	uint32_t spawn = 0;
 	shadeWhitted<R, 0, F>(sc, ft, nd.shader, ray.dir, task.depth, h, task.weight, rng, spawn, ws, accum, cnt);
+}
+
+// Takes the top entry off the ray-task stack and traces it. `primary` is the stream of the pixel sample (branch 0), which
+// the primary invocation draws from directly; every other invocation owns the derived stream recorded in its task.
+template <typename R, int F>
+FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, Rng& primary, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
+{
+	const RayTask<R> t = ws.stack[--ws.sp];
+	if (t.kind == FRAY_TASK_GLOSSY) {
+		// sample t.k of a glossy reflection: Reflection::shade, src/shading.cpp:176-200
+		const DShader<R>& s = sc.shaders[t.shader];
+		Rng child;
+		child.init(primary.seed, primary.pixel, primary.sample, rngChildBranch(t.branch, t.count, t.k0 + (uint32_t) t.k));
+		V3<R> b, c;
+		orthonormalSystem(t.n, b, c);
+		V3<R> reflected;
+		for (;;) {
+			// Random::unitDiscSample, src/random_generator.cpp:71-80
+			R sn, cs;
+			Num<R>::sincos2pi(Num<R>::draw(child), sn, cs);
+			const R rad = Num<R>::sqrtR(Num<R>::draw(child));
+			const R x = sn * rad * s.deflectionScaling, y = cs * rad * s.deflectionScaling;
+			const V3<R> nn = normalized(t.n + b * x + c * y);
+			reflected = reflect(t.dir, nn);
+			if (dot(reflected, t.n) > 0) break;
+		}
+		if (t.k + 1 < t.ns) { // the remaining samples go back under whatever this one spawns
+			ws.stack[ws.sp] = t;
+			ws.stack[ws.sp].k = t.k + 1;
+			ws.sp++;
+		}
+		RayTask<R> ray;
+		ray.kind = FRAY_TASK_RAY;
+		ray.start = t.start;
+		ray.dir = reflected;
+		ray.weight = t.weight;
+		ray.depth = t.depth + 1;
+		ray.branch = child.branch;
+		ray.count = child.count;
+		whittedStep<R, F>(sc, ft, ray, child, ws, accum, cnt);
+		return;
+	}
+	if (t.branch == 0) {
+		whittedStep<R, F>(sc, ft, t, primary, ws, accum, cnt);
+	} else {
+		Rng child;
+		child.init(primary.seed, primary.pixel, primary.sample, t.branch);
+		child.skip(t.count);
+		whittedStep<R, F>(sc, ft, t, child, ws, accum, cnt);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1530,22 +1578,17 @@ FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, 
 			ps.flags = 0;
 			while (pathSegment<R, F>(sc, ft, ps, rng, c, cnt)) {}
 		} else {
-			ws->sp = 0;
 			RayTask<R> root;
+			root.kind = FRAY_TASK_RAY;
 			root.start = rays[e].start;
 			root.dir = rays[e].dir;
 			root.weight = Col(1, 1, 1);
 			root.depth = 0;
 			root.branch = 0;
 			root.count = 0;
-			whittedStep<R, F>(sc, ft, root, rng, *ws, c, cnt); // the primary invocation draws from the pixel sample's own stream
-			while (ws->sp > 0) {
-				const RayTask<R> t = ws->stack[--ws->sp];
-				Rng child;
-				child.init(seed, rng.pixel, rng.sample, t.branch);
-				child.skip(t.count);
-				whittedStep<R, F>(sc, ft, t, child, *ws, c, cnt);
-			}
+			ws->stack[0] = root;
+			ws->sp = 1;
+			while (ws->sp > 0) whittedPop<R, F>(sc, ft, rng, *ws, c, cnt);
 		}
 		if (stereo) {
 			if (sc.saturation != 1) c = adjustSaturation(c, sc.saturation);

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : (Num<R>::k
 			} else {
 				RayTask<R> root;
 				root.start = first.start; root.dir = first.dir; root.weight = Col(1, 1, 1);
-				root.depth = 0; root.branch = 0; root.count = 0;
+				root.depth = 0; root.branch = 0; root.count = 0; root.kind = FRAY_TASK_RAY;
 				ws.stack[0] = root;
 				ws.sp = 1;
 			}
@@ -180,15 +180,7 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : (Num<R>::k
 			if (GI) {
 				finished = !pathSegment<R, F>(sc, ft, ps, rng, eyeCol, cnt);
 			} else {
-				const RayTask<R> t = ws.stack[--ws.sp];
-				if (t.branch == 0) {
-					whittedStep<R, F>(sc, ft, t, rng, ws, eyeCol, cnt); // primary invocation: the sample's own stream
-				} else {
-					Rng child;
-					child.init(p.seed, rng.pixel, rng.sample, t.branch);
-					child.skip(t.count);
-					whittedStep<R, F>(sc, ft, t, child, ws, eyeCol, cnt);
-				}
+				whittedPop<R, F>(sc, ft, rng, ws, eyeCol, cnt);
 				finished = ws.sp == 0;
 			}
 			if (finished) {
@@ -206,7 +198,7 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : (Num<R>::k
 					} else {
 						RayTask<R> root;
 						root.start = rightEye.start; root.dir = rightEye.dir; root.weight = Col(1, 1, 1);
-						root.depth = 0; root.branch = 0; root.count = 0;
+						root.depth = 0; root.branch = 0; root.count = 0; root.kind = FRAY_TASK_RAY;
 						ws.stack[0] = root;
 						ws.sp = 1;
 					}

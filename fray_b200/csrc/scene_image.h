@@ -508,10 +508,7 @@ template <typename R> struct SceneImage {
 					if (!inRange(L.shader, s.num_shaders) || L.texture >= s.num_textures) { err = "layer references out of range"; return false; }
 				}
 			}
-			if (sh.type == FRAY_SHADER_REFL && !sh.pure_reflection && sh.num_samples > FRAY_TASK_STACK - 16) {
-				err = "glossy numSamples exceeds the device ray-task stack";
-				return false;
-			}
+			if (sh.type == FRAY_SHADER_REFL && !sh.pure_reflection && sh.num_samples < 1) { err = "glossy numSamples must be >= 1"; return false; }
 		}
 		for (int i = 0; i < s.num_shaders; i++)
 			if (layeredDepth(s, i, 0) > 2) { err = "Layered shaders nested deeper than 2 are not supported"; return false; }

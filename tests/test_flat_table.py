@@ -60,3 +60,91 @@ def test_flat_table_on_the_gpu(scene):
     want, ostats = ou.oracle_render(scene, seed=7)
     got, stats = render(scene, fb.FP64, seed=7)
     assert ou.compare(want, got, 2e-5)[0] == 1.0 and stats.rays == ostats.rays
+
+
+# ---- degenerate inputs: nothing to hit, nothing to light with, frames that are not a multiple of the 8x4 tile ----
+EMPTY = """
+GlobalSettings {
+	frameWidth 37
+	frameHeight 21
+	wantAA on
+}
+Camera camera {
+	position (0, 1, -5)
+	fov 60
+}
+"""
+
+NO_LIGHTS_GI = """
+GlobalSettings {
+	frameWidth 13
+	frameHeight 9
+	gi on
+	pathsPerPixel 6
+	maxTraceDepth 3
+}
+Camera camera {
+	position (0, 2, -6)
+	pitch -10
+	fov 60
+}
+Plane floor {
+	y 0
+	limit 30
+}
+Sphere ball {
+	O (0, 1, 0)
+	R 1
+}
+Lambert grey {
+	color (0.6, 0.6, 0.6)
+}
+Refl mirror {
+	multiplier 0.8
+}
+Node floor {
+	geometry floor
+	shader grey
+}
+Node ball {
+	geometry ball
+	shader mirror
+}
+"""
+
+
+def _edge_cases(tmp_path, render, exact_tol):
+    for name, text in (("empty", EMPTY), ("nolights", NO_LIGHTS_GI)):
+        p = tmp_path / f"{name}.fray"
+        p.write_text(text)
+        sc = fb.Scene(str(p))
+        want, ostats = ou.oracle_render(sc, seed=3)
+        for precision, tol in ((fb.FP64, exact_tol), (fb.FP32, 1e-3)):
+            got, stats = render(sc, precision, seed=3)
+            assert got.shape == (sc.height, sc.width, 3) and np.isfinite(got).all()
+            frac, rmse, mx = ou.compare(want, got, tol)
+            assert frac >= (1.0 if precision == fb.FP64 else 0.98), (name, precision, frac, rmse, mx)
+            assert stats.primary_rays == ostats.primary_rays == sc.width * sc.height * sc.spp
+            if precision == fb.FP64:
+                assert stats.rays == ostats.rays
+        if name == "empty":
+            assert not want.any()  # no environment: black (src/main.cpp:272-276)
+        # shards of a frame whose size is not a multiple of the tile still add up
+        full, fs = render(sc, fb.FP32, seed=3, flags=fb.FRAME_SUM)
+        parts = [render(sc, fb.FP32, seed=3, flags=fb.FRAME_SUM, bucket_rank=r, bucket_count=3) for r in range(3)]
+        assert np.array_equal(sum(q[0] for q in parts), full) and sum(q[1].rays for q in parts) == fs.rays
+
+
+def test_edge_cases_on_the_host_emulator(tmp_path):
+    from test_emul_vs_oracle import emul as emul_fixture
+    _edge_cases(tmp_path, emul_fixture.__wrapped__(), 1e-5)
+
+
+@pytest.mark.gpu
+def test_edge_cases_on_the_gpu(tmp_path):
+    def render(sc, precision, **kw):
+        ctx = fb.GpuContext(sc, 0, precision)
+        out = ctx.render(**kw)
+        ctx.close()
+        return out
+    _edge_cases(tmp_path, render, 2e-5)
