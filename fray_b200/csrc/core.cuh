@@ -47,7 +47,7 @@ template <> struct Num<double> {
 		s = sin(a);
 		c = cos(a);
 	}
-	FRAY_HD static double draw(Rng& rng) { return rng.randdouble(); }
+	template <typename RNG> FRAY_HD static double draw(RNG& rng) { return rng.randdouble(); }
 	FRAY_HD static float overPi(float c) { return (float) (c / 3.141592653589793238); } // `cosTerm / PI` is a double division
 	FRAY_HD static double big() { return 1e99; }                                        // INF, src/constants.h:32
 };
@@ -87,7 +87,7 @@ template <> struct Num<float> {
 		c = cosf(6.28318530717958647692f * u);
 #endif
 	}
-	FRAY_HD static float draw(Rng& rng) { return rng.randdoubleAsFloat(); }
+	template <typename RNG> FRAY_HD static float draw(RNG& rng) { return rng.randdoubleAsFloat(); }
 	FRAY_HD static float overPi(float c) { return c * 0.318309886183790672f; }
 	FRAY_HD static float big() { return FLT_MAX; }
 };
@@ -252,6 +252,9 @@ template <typename R> struct DScene {
 	int shadowFirst[FRAY_SHADOW_LIGHTS], shadowCount[FRAY_SHADOW_LIGHTS];
 	int numFlatTotal;          // records in flatPolys including the shadow sets (what the kernels stage)
 	int numFlatSpheres;        // (centre, R^2) vectors that follow the records in flatPolys; their FlatInfo follow the lights'
+	int numFlatHex;            // convex hexahedra (FRAY_HEX_VEC vectors each) after the spheres; FlatInfo of their faces after the spheres'
+	int numFlatInfo;           // all FlatInfo entries
+	unsigned shadowHex[FRAY_SHADOW_LIGHTS]; // bit k: hexahedron k can occlude a ray towards light l
 };
 
 template <typename R> struct Ray {
@@ -787,19 +790,21 @@ template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
 #define FRAY_F_FLAT 8   // fast precision: the flat polygon table (flat.cuh) holds the brute-force meshes and the lights
 #define FRAY_F_ATTR 16  // some flat record interpolates normals / uvs
 #define FRAY_F_SPHERES 32 // the flat table has a sphere list
+#define FRAY_F_HEX 64     // the flat table has convex hexahedra
 #define FRAY_F_GENERIC (FRAY_F_NODES | FRAY_F_TEX)
 
 // The kernel variants compiled per precision, smallest first; a scene runs on the first one that covers its feature bits.
 template <typename R> struct Variants;
 template <> struct Variants<float> {
 	static constexpr int count = 5;
+	static constexpr int kLean = FRAY_F_FLAT | FRAY_F_HEX;
 	static constexpr int mask(int i)
 	{
-		return i == 0 ? FRAY_F_FLAT                                                      // brute-force meshes, planes, lights (cornell_box)
-		     : i == 1 ? (FRAY_F_FLAT | FRAY_F_SPHERES)                                     // + translated spheres (smallpt)
-		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
-		     : i == 3 ? (FRAY_F_FLAT | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX) // everything but CSG
-		              : (FRAY_F_FLAT | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
+		return i == 0 ? kLean                                                      // brute-force meshes, planes, lights (cornell_box)
+		     : i == 1 ? (kLean | FRAY_F_SPHERES)                                     // + translated spheres (smallpt)
+		     : i == 2 ? (kLean | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
+		     : i == 3 ? (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX) // everything but CSG
+		              : (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
 	}
 };
 template <> struct Variants<double> {
@@ -812,6 +817,7 @@ struct FlatTab {
 	const float4* polys;
 	const FlatInfo* info;
 	const float4* spheres;
+	const float4* hexes;
 };
 
 // Node::intersect, src/geometry.cpp:196-208. On success h is in WORLD space (ip, norm, dist).
@@ -870,6 +876,10 @@ template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const
 			count = sc.shadowCount[light];
 		}
 		if (flatAny(ft.polys + FRAY_FLAT_POLY_VEC * first, count, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		if (F & FRAY_F_HEX) {
+			const unsigned hexMask = (light >= 0 && light < FRAY_SHADOW_LIGHTS) ? sc.shadowHex[light] : 0xffffffffu;
+			if (flatHexAny(ft.hexes, sc.numFlatHex, hexMask, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		}
 		if ((F & FRAY_F_SPHERES) && flatSpheresAny(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 	}
 	if (F & FRAY_F_NODES) {
@@ -920,6 +930,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 	if constexpr ((F & FRAY_F_FLAT) != 0 && !Num<R>::kExact) {
 		int idx = -1;
 		flatClosest(ft.polys, sc.numFlatAll, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
+		if (F & FRAY_F_HEX) flatHexClosest(ft.hexes, sc.numFlatHex, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
 		if (F & FRAY_F_SPHERES) flatSpheresClosest(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx, sc.numFlatAll);
 		if (idx >= 0) {
 			const FlatInfo& fi = ft.info[idx];
@@ -1086,8 +1097,8 @@ template <typename R> FRAY_HD int lightNumSamples(const DLight<R>& l) { return l
 template <typename R> FRAY_HD Col lightEmission(const DLight<R>& l) { return loadCol(l.color) * l.power; } // Light::getColor
 
 // PointLight::getNthSample src/lights.cpp:31-35; RectLight::getNthSample src/lights.cpp:49-77
-template <typename R>
-FRAY_HD void lightSample(const DLight<R>& l, Rng& rng, int sampleIdx, const V3<R>& shadePos, V3<R>& samplePos, Col& color, bool wantColor)
+template <typename R, typename RNG>
+FRAY_HD void lightSample(const DLight<R>& l, RNG& rng, int sampleIdx, const V3<R>& shadePos, V3<R>& samplePos, Col& color, bool wantColor)
 {
 	if (l.type == FRAY_LIGHT_POINT) {
 		samplePos = load3(l.pos);
@@ -1116,8 +1127,8 @@ FRAY_HD void lightSample(const DLight<R>& l, Rng& rng, int sampleIdx, const V3<R
 // ---------------------------------------------------------------------------------------------------
 // Whitted shading: local terms (Lambert / Phong), src/shading.cpp:48-80, 101-144
 // ---------------------------------------------------------------------------------------------------
-template <typename R, int F>
-FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, Rng& rng, RayCounters& cnt)
+template <typename R, int F, typename RNG>
+FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
 {
 	Col diffuse = loadCol(s.color);
 	if ((F & FRAY_F_TEX) && s.texture >= 0) diffuse = diffuse * sampleTexture(sc, s.texture, rayDir, h.norm, h.u, h.v);
@@ -1204,9 +1215,9 @@ template <typename R> struct WhittedState {
 // Reflection::shade (src/shading.cpp:160-205), Refraction::shade (:238-263), Layered::shade (:357-367), expressed as
 // "add weight * local shading now, push weight' * raytrace(child) for later". `spawn` numbers the children of this
 // raytrace() invocation in the order the reference would create them (RNG contract).
-template <typename R, int LEVEL, int F>
+template <typename R, int LEVEL, int F, typename RNG>
 FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx, const V3<R>& rayDir, int depth, const Hit<R>& h, const Col& weight,
-                          Rng& rng, uint32_t& spawn, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
+                          RNG& rng, uint32_t& spawn, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
 	const DShader<R>& s = sc.shaders[shaderIdx];
 	switch (s.type) {
@@ -1282,8 +1293,8 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 
 // raytrace(), src/main.cpp:246-285: one ray of the Whitted tree. Adds weight * (what this invocation returns minus
 // what its secondary rays return) to accum and pushes the secondary rays.
-template <typename R, int F>
-FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R>& task, Rng& rng, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
+template <typename R, int F, typename RNG>
+FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R>& task, RNG& rng, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
 	if (task.depth > sc.maxTraceDepth) return;
 	cnt.rays++;
@@ -1306,14 +1317,14 @@ FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R
 
 // Takes the top entry off the ray-task stack and traces it. `primary` is the stream of the pixel sample (branch 0), which
 // the primary invocation draws from directly; every other invocation owns the derived stream recorded in its task.
-template <typename R, int F>
-FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, Rng& primary, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
+template <typename R, int F, typename RNG>
+FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, RNG& primary, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
 	const RayTask<R> t = ws.stack[--ws.sp];
 	if (t.kind == FRAY_TASK_GLOSSY) {
 		// sample t.k of a glossy reflection: Reflection::shade, src/shading.cpp:176-200
 		const DShader<R>& s = sc.shaders[t.shader];
-		Rng child;
+		RNG child;
 		child.init(primary.seed, primary.pixel, primary.sample, rngChildBranch(t.branch, t.count, t.k0 + (uint32_t) t.k));
 		V3<R> b, c;
 		orthonormalSystem(t.n, b, c);
@@ -1347,7 +1358,7 @@ FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, Rng& primary, Wh
 	if (t.branch == 0) {
 		whittedStep<R, F>(sc, ft, t, primary, ws, accum, cnt);
 	} else {
-		Rng child;
+		RNG child;
 		child.init(primary.seed, primary.pixel, primary.sample, t.branch);
 		child.skip(t.count);
 		whittedStep<R, F>(sc, ft, t, child, ws, accum, cnt);
@@ -1367,7 +1378,7 @@ template <typename R> struct PathState {
 };
 
 // hemisphereSample(), src/main.cpp:92-116. cos(phi) = 2v-1 and sin(phi) = sqrt(1 - cos^2) replace acos/sin/cos.
-template <typename R> FRAY_HD V3<R> hemisphereSample(Rng& rng, const V3<R>& norm)
+template <typename R, typename RNG> FRAY_HD V3<R> hemisphereSample(RNG& rng, const V3<R>& norm)
 {
 	const R u = Num<R>::draw(rng);
 	const R v = Num<R>::draw(rng);
@@ -1389,7 +1400,7 @@ template <typename R> FRAY_HD bool pathAlive(const DScene<R>& sc, const PathStat
 // (contribLight of every level and the terminal term); FP32 summation order differs from the recursion's unwinding.
 // The cut-off of the NEXT level is evaluated at the end of this one, so that a lane whose path is over learns it in
 // the same iteration and never spends a whole trip round the warp loop just to find out.
-template <typename R, int F> FRAY_HD bool pathSegment(const DScene<R>& sc, const FlatTab& ft, PathState<R>& ps, Rng& rng, Col& accum, RayCounters& cnt)
+template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene<R>& sc, const FlatTab& ft, PathState<R>& ps, RNG& rng, Col& accum, RayCounters& cnt)
 {
 	if (!pathAlive(sc, ps)) return false; // only the first level can fail here (maxTraceDepth < 0)
 	cnt.rays++;
@@ -1511,7 +1522,7 @@ template <typename R> FRAY_HD Ray<R> screenRay(const DCamera<R>& c, R x, R y, in
 	return r;
 }
 
-template <typename R> FRAY_HD Ray<R> dofRay(const DCamera<R>& c, Rng& rng, R x, R y, int which)
+template <typename R, typename RNG> FRAY_HD Ray<R> dofRay(const DCamera<R>& c, RNG& rng, R x, R y, int which)
 {
 	Ray<R> ray = screenRay(c, x, y, which);
 	const R M = c.focalDist / dot(load3(c.front), ray.dir);
@@ -1525,7 +1536,7 @@ template <typename R> FRAY_HD Ray<R> dofRay(const DCamera<R>& c, Rng& rng, R x, 
 	return ray;
 }
 
-template <typename R> FRAY_HD Ray<R> cameraRay(const DCamera<R>& c, Rng& rng, R x, R y, int which) // getRay, src/main.cpp:296-302
+template <typename R, typename RNG> FRAY_HD Ray<R> cameraRay(const DCamera<R>& c, RNG& rng, R x, R y, int which) // getRay, src/main.cpp:296-302
 {
 	return c.dof ? dofRay(c, rng, x, y, which) : screenRay(c, x, y, which);
 }
@@ -1537,7 +1548,7 @@ FRAY_HD Col adjustSaturation(const Col& c, float amount) // src/color.h:128-134
 }
 
 // pixel-sample offsets, src/main.cpp:55-61 and :351-357
-FRAY_HD void sampleOffset(bool randomOffsets, int sampleIdx, Rng& rng, float& ox, float& oy)
+template <typename RNG> FRAY_HD void sampleOffset(bool randomOffsets, int sampleIdx, RNG& rng, float& ox, float& oy)
 {
 	if (randomOffsets) {
 		ox = rng.randfloat();

@@ -61,13 +61,14 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 {
 	extern __shared__ float4 flatSmem[];
 	FlatTab ft;
-	// layout: records (incl. shadow sets) | spheres | FlatInfo (records, lights, spheres)
-	const int nVec = FRAY_FLAT_POLY_VEC * sc.numFlatTotal + sc.numFlatSpheres;
+	// layout: records (incl. shadow sets) | spheres | hexahedra | FlatInfo (records, lights, spheres, hexahedron faces)
+	const int nVec = FRAY_FLAT_POLY_VEC * sc.numFlatTotal + sc.numFlatSpheres + FRAY_HEX_VEC * sc.numFlatHex;
 	ft.polys = flatSmem;
 	ft.spheres = flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatTotal;
+	ft.hexes = ft.spheres + sc.numFlatSpheres;
 	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + nVec);
 	if (F & FRAY_F_FLAT) {
-		const int nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * (sc.numFlatAll + sc.numFlatSpheres);
+		const int nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * sc.numFlatInfo;
 		const float4* gi = reinterpret_cast<const float4*>(sc.flatInfo);
 		for (int i = threadIdx.x; i < nVec; i += blockDim.x) flatSmem[i] = sc.flatPolys[i];
 		for (int i = threadIdx.x; i < nInfo; i += blockDim.x) flatSmem[nVec + i] = gi[i];
@@ -77,7 +78,7 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 }
 
 template <typename R, bool GI, int F>
-__global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : (Num<R>::kExact ? 1 : (GI ? 6 : 5))) renderKernel(const DScene<R> sc, const RenderParams p)
+__global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 : (Num<R>::kExact ? 1 : (GI ? 6 : 5))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(128, (F == FRAY_F_FLAT && GI) ? 6 : (Num<R>::k
 	int cur = 0, end = 0;  // next sample / end of the chunk
 	Col accum(0, 0, 0);    // sum over the finished samples of the chunk
 	Col eyeCol(0, 0, 0);   // radiance of the path / ray tree in flight
-	Rng rng;               // stream of the sample in flight (branch 0)
+	RngT<(GI && F == Variants<float>::kLean)> rng; // stream of the sample in flight (branch 0)
 	PathState<R> ps;
 	Ray<R> rightEye;       // stereo: the second ray is generated up front (src/main.cpp:307-308) and traced afterwards
 	int eye = 0;
@@ -250,7 +251,7 @@ struct LaunchConfig {
 
 template <typename R> inline size_t flatSmemBytes(const DScene<R>& sc)
 {
-	return ((size_t) sc.numFlatTotal * FRAY_FLAT_POLY_VEC + sc.numFlatSpheres) * sizeof(float4) + (size_t) (sc.numFlatAll + sc.numFlatSpheres) * sizeof(FlatInfo);
+	return ((size_t) sc.numFlatTotal * FRAY_FLAT_POLY_VEC + sc.numFlatSpheres + (size_t) sc.numFlatHex * FRAY_HEX_VEC) * sizeof(float4) + (size_t) sc.numFlatInfo * sizeof(FlatInfo);
 }
 
 // one launch of the render (or AOV) kernel for precision R; defined in render_fp32.cu / render_fp64.cu

@@ -60,6 +60,19 @@ FRAY_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
 	return Philox4{ c0, c1, c2, c3 };
 }
 
+// One block of a stream. On the GPU this is ONE out-of-line copy per kernel (arguments and result travel in registers):
+// the ten rounds are ~60 instructions, a path segment needs three blocks and a new sample one, and four inlined copies
+// were what pushed the hot loop of the path tracer out of the 32 KB instruction cache.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+Philox4 philoxBlock(uint32_t block, uint32_t pixel, uint32_t sample, uint32_t branch, uint32_t seed)
+{
+	return philox4x32_10(block, pixel, sample, branch, seed, 0x46524159u);
+}
+
 FRAY_HD uint32_t rngMix(uint32_t v)
 {
 	v = (v ^ (v >> 16)) * 0x7FEB352Du;
@@ -73,7 +86,9 @@ FRAY_HD uint32_t rngChildBranch(uint32_t branch, uint32_t draws, uint32_t k)
 	return rngMix(branch ^ rngMix(draws * 0x9E3779B9u + k + 1u)) | 1u;
 }
 
-struct Rng {
+// OUTLINE: generate blocks through the out-of-line philoxBlock (the lean path-tracing kernel, whose hot loop has to fit the
+// instruction cache) instead of inlining the ten rounds at every use (everything else: the call costs ~4 % there)
+template <bool OUTLINE> struct RngT {
 	uint32_t seed, pixel, sample, branch;
 	uint32_t count; // draws consumed
 	Philox4 blk;    // block ((count - 1) >> 2) when count & 3
@@ -82,7 +97,11 @@ struct Rng {
 	{
 		seed = seed_; pixel = pixel_; sample = sample_; branch = branch_; count = 0;
 	}
-	FRAY_HD void refill() { blk = philox4x32_10(count >> 2, pixel, sample, branch, seed, 0x46524159u); }
+	FRAY_HD void refill()
+	{
+		if (OUTLINE) blk = philoxBlock(count >> 2, pixel, sample, branch, seed);
+		else blk = philox4x32_10(count >> 2, pixel, sample, branch, seed, 0x46524159u);
+	}
 	FRAY_HD uint32_t next()
 	{
 		const uint32_t lane = count & 3u;
@@ -117,5 +136,7 @@ struct Rng {
 		return a + (int) mulhi32(next(), n);
 	}
 };
+
+typedef RngT<false> Rng;
 
 } // namespace fray

@@ -10,6 +10,9 @@
 //   * relative indices -> absolute, identity transforms flagged, "does anything on this node read (u,v)" flagged
 #pragma once
 #include <algorithm>
+#include <array>
+#include <functional>
+#include <map>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -124,6 +127,162 @@ template <typename R> struct SceneImage {
 		}
 	}
 
+
+	// the points that span a light: the corners of a RectLight's unit square in world space, or the PointLight's position
+	static std::vector<D3> lightPoints(const FrayGpuLight& l)
+	{
+		std::vector<D3> pts;
+		if (l.type == FRAY_LIGHT_RECT) {
+			const D3 off{ l.T.offset[0], l.T.offset[1], l.T.offset[2] };
+			for (int k = 0; k < 4; k++) {
+				const D3 q = rowMul(D3{ (k & 1) ? 0.5 : -0.5, 0, (k & 2) ? 0.5 : -0.5 }, l.T.m);
+				pts.push_back(D3{ q.x + off.x, q.y + off.y, q.z + off.z });
+			}
+		} else {
+			pts.push_back(D3{ l.pos[0], l.pos[1], l.pos[2] });
+		}
+		return pts;
+	}
+	// can the plane (Nu, d) have any point of the light behind it (i.e. can a front-face hit shadow that light at all)?
+	static bool lightBehind(const D3& Nu, double d, const std::vector<D3>& pts)
+	{
+		double behind = 1e300, scale = fabs(d) + 1;
+		for (const D3& q: pts) {
+			behind = std::min(behind, dt(Nu, q) - d);
+			scale = std::max(scale, std::max(fabs(q.x), std::max(fabs(q.y), fabs(q.z))));
+		}
+		return behind < 1e-4 * scale; // otherwise the whole light is clearly in front
+	}
+
+	// a flat record of a brute-force mesh before it is emitted, with what the hexahedron search needs
+	struct Cand {
+		float4 rec[5];
+		FlatInfo fi;
+		std::vector<D3> v; // polygon vertices
+		D3 Nu;             // unit plane normal (front side)
+		double d;          // Nu . p = d on the plane
+		bool twoSided, attr;
+		int hex;           // index of the hexahedron that swallowed the record, or -1
+	};
+	struct Hex {
+		std::vector<int> faces;                       // candidate indices: the real faces
+		std::vector<std::pair<D3, double>> caps;      // planes that close an open boundary loop: they clip, but cannot be hit
+	};
+
+	// Convex hexahedra (flat.cuh): connected groups of one-sided, faceted records that are ALL the faces of a convex polyhedron
+	// seen from outside, with at most FRAY_HEX_PLANES planes including the caps of planar boundary loops.
+	void findHexes(std::vector<Cand>& cands, std::vector<Hex>& hexes)
+	{
+		const int n = (int) cands.size();
+		std::map<std::array<double, 3>, int> vid; // vertex ids by exact position
+		std::vector<D3> vpos;
+		std::map<std::pair<int, int>, std::vector<int>> edges; // undirected edge -> faces using it
+		std::vector<std::vector<int>> cv(n);
+		for (int c = 0; c < n; c++) {
+			if (cands[c].twoSided || cands[c].attr) continue;
+			for (const D3& p: cands[c].v) {
+				const std::array<double, 3> key{ p.x, p.y, p.z };
+				auto it = vid.find(key);
+				if (it == vid.end()) {
+					it = vid.emplace(key, (int) vpos.size()).first;
+					vpos.push_back(p);
+				}
+				cv[c].push_back(it->second);
+			}
+			for (size_t k = 0; k < cv[c].size(); k++) {
+				const int a = cv[c][k], b = cv[c][(k + 1) % cv[c].size()];
+				edges[{ std::min(a, b), std::max(a, b) }].push_back(c);
+			}
+		}
+		std::vector<int> parent(n);
+		for (int i = 0; i < n; i++) parent[i] = i;
+		std::function<int(int)> find = [&](int x) { return parent[x] == x ? x : parent[x] = find(parent[x]); };
+		for (auto& e: edges)
+			for (size_t k = 1; k < e.second.size(); k++) parent[find(e.second[k])] = find(e.second[0]);
+		std::map<int, std::vector<int>> comps;
+		for (int c = 0; c < n; c++)
+			if (!cv[c].empty()) comps[find(c)].push_back(c);
+
+		for (auto& kv: comps) {
+			const std::vector<int>& members = kv.second;
+			if (members.size() < 3 || members.size() > FRAY_HEX_PLANES || (int) hexes.size() >= FRAY_MAX_HEX) continue;
+			std::vector<int> verts;
+			double extent = 0;
+			for (int c: members)
+				for (int id: cv[c]) {
+					verts.push_back(id);
+					extent = std::max(extent, std::max(fabs(vpos[id].x), std::max(fabs(vpos[id].y), fabs(vpos[id].z))));
+				}
+			const double tol = 1e-9 * (extent + 1), ctol = 1e-7 * (extent + 1);
+			// convex and seen from outside: every vertex on or behind every face plane; no two faces in one plane
+			bool ok = true;
+			for (int c: members)
+				for (int id: verts)
+					if (dt(cands[c].Nu, vpos[id]) - cands[c].d > tol) ok = false;
+			for (size_t i = 0; i < members.size() && ok; i++)
+				for (size_t j = i + 1; j < members.size(); j++)
+					if (dt(cands[members[i]].Nu, cands[members[j]].Nu) > 1 - 1e-12) ok = false;
+			if (!ok) continue;
+			// every edge shared by exactly two faces, or on the boundary
+			std::map<int, std::vector<int>> boundary; // vertex -> boundary neighbours
+			for (int c: members)
+				for (size_t k = 0; k < cv[c].size(); k++) {
+					const int a = cv[c][k], b = cv[c][(k + 1) % cv[c].size()];
+					const size_t users = edges[{ std::min(a, b), std::max(a, b) }].size();
+					if (users > 2) ok = false;
+					if (users == 1) { boundary[a].push_back(b); boundary[b].push_back(a); }
+				}
+			// boundary loops -> cap planes, oriented outwards like the faces
+			std::vector<std::pair<D3, double>> caps;
+			std::map<int, bool> seen;
+			for (auto& bv: boundary) {
+				if (!ok) break;
+				if (seen[bv.first]) continue;
+				std::vector<int> loop;
+				int prev = -1, cur = bv.first;
+				while (ok && !seen[cur]) {
+					seen[cur] = true;
+					loop.push_back(cur);
+					const std::vector<int>& nb = boundary[cur];
+					if (nb.size() != 2) { ok = false; break; }
+					const int next = nb[0] != prev ? nb[0] : nb[1];
+					prev = cur;
+					cur = next;
+				}
+				if (!ok || loop.size() < 3) { ok = false; break; }
+				D3 N{ 0, 0, 0 }; // Newell normal of the loop
+				for (size_t k = 0; k < loop.size(); k++) {
+					const D3 &a = vpos[loop[k]], &b = vpos[loop[(k + 1) % loop.size()]];
+					N.x += (a.y - b.y) * (a.z + b.z);
+					N.y += (a.z - b.z) * (a.x + b.x);
+					N.z += (a.x - b.x) * (a.y + b.y);
+				}
+				const double l = sqrt(dt(N, N));
+				if (!(l > 0)) { ok = false; break; }
+				N = scl(N, 1 / l);
+				double dcap = dt(N, vpos[loop[0]]);
+				for (int id: loop)
+					if (fabs(dt(N, vpos[id]) - dcap) > ctol) ok = false; // the loop is not planar
+				double lo = 0, hi = 0;
+				for (int id: verts) {
+					lo = std::min(lo, dt(N, vpos[id]) - dcap);
+					hi = std::max(hi, dt(N, vpos[id]) - dcap);
+				}
+				if (hi > ctol && lo < -ctol) ok = false; // the solid sticks out on both sides of the loop's plane
+				else if (hi > ctol) { N = scl(N, -1); dcap = -dcap; }
+				for (int c: members)
+					if (dt(cands[c].Nu, N) > 1 - 1e-12) ok = false; // a cap in (or parallel behind) a face plane: leave the mesh alone
+				caps.emplace_back(N, dcap);
+			}
+			if (!ok || members.size() + caps.size() > FRAY_HEX_PLANES || members.size() + caps.size() < 4) continue;
+			Hex hx;
+			hx.faces = members;
+			hx.caps = caps;
+			for (int c: members) cands[c].hex = (int) hexes.size();
+			hexes.push_back(hx);
+		}
+	}
+
 	// Fills flatPolys / flatInfo and marks the nodes whose geometry moved into the table. Returns the feature bits used.
 	int buildFlat(const FrayGpuScene& s, std::vector<DNode<R>>& nodes)
 	{
@@ -137,6 +296,7 @@ template <typename R> struct SceneImage {
 		int room = FRAY_MAX_FLAT - numRect;
 		std::vector<float4> spheres;
 		std::vector<FlatInfo> sphereInfo;
+		std::vector<Cand> cands;
 
 		for (int ni = 0; ni < s.num_nodes; ni++) {
 			const FrayGpuNode& n = s.nodes[ni];
@@ -213,10 +373,8 @@ template <typename R> struct SceneImage {
 				return D3{ p.x + off.x, p.y + off.y, p.z + off.z };
 			};
 			// records of this node, built first so that a node is flattened completely or not at all
-			std::vector<float4> recs;
-			std::vector<FlatInfo> infos;
-			bool ok = true;
-			for (int t = 0; t < m.num_triangles && ok; t++) {
+			std::vector<Cand> mine;
+			for (int t = 0; t < m.num_triangles; t++) {
 				const size_t ti = (size_t) m.first_triangle + t;
 				const D3 A = world(t, 0), B = world(t, 1), C = world(t, 2);
 				D3 N = crs(sub(B, A), sub(C, A));
@@ -282,18 +440,30 @@ template <typename R> struct SceneImage {
 					if (!edgePlane(A, C, N, B, rec[1]) || !edgePlane(A, B, N, C, rec[2]) || !edgePlane(B, C, N, A, rec[3])) continue;
 					rec[4] = always;
 				}
-				for (int k = 0; k < 5; k++) recs.push_back(rec[k]);
-				infos.push_back(fi);
+				Cand cd;
+				for (int k = 0; k < 5; k++) cd.rec[k] = rec[k];
+				cd.fi = fi;
+				cd.v = merged ? std::vector<D3>{ A, B, C, world(t + 1, 2) } : std::vector<D3>{ A, B, C };
+				cd.Nu = Nu;
+				cd.d = dt(Nu, A);
+				cd.twoSided = !cull;
+				cd.attr = attr;
+				cd.hex = -1;
+				mine.push_back(cd);
 				if (merged) t++;
 			}
-			const int count = (int) infos.size() * (cull ? 1 : 2);
-			if (!ok || count > room) continue;
+			const int count = (int) mine.size() * (cull ? 1 : 2);
+			if (count > room) continue;
 			room -= count;
-			for (size_t k = 0; k < infos.size(); k++) pushFlat(&recs[5 * k], infos[k], !cull);
+			cands.insert(cands.end(), mine.begin(), mine.end());
 			nodes[ni].inFlat = 1;
 			feat |= FRAY_F_FLAT;
 			if (attr) feat |= FRAY_F_ATTR;
 		}
+		std::vector<Hex> hexes;
+		if (!getenv("FRAY_GPU_NO_HEX")) findHexes(cands, hexes);
+		for (const Cand& cd: cands)
+			if (cd.hex < 0) pushFlat(cd.rec, cd.fi, cd.twoSided);
 		offsets.numFlatGeom = (int) flatInfo.size();
 		// lights: the unit square of light space, seen from its -y side by rays travelling towards +y (src/lights.cpp:79-103)
 		for (int li = 0; li < s.num_lights; li++) {
@@ -323,25 +493,11 @@ template <typename R> struct SceneImage {
 		int shadowRoom = FRAY_MAX_SHADOW;
 		for (int li = 0; li < s.num_lights && li < FRAY_SHADOW_LIGHTS; li++) {
 			const FrayGpuLight& l = s.lights[li];
-			std::vector<D3> pts;
-			if (l.type == FRAY_LIGHT_RECT) {
-				const D3 off{ l.T.offset[0], l.T.offset[1], l.T.offset[2] };
-				for (int k = 0; k < 4; k++) {
-					const D3 q = rowMul(D3{ (k & 1) ? 0.5 : -0.5, 0, (k & 2) ? 0.5 : -0.5 }, l.T.m);
-					pts.push_back(D3{ q.x + off.x, q.y + off.y, q.z + off.z });
-				}
-			} else {
-				pts.push_back(D3{ l.pos[0], l.pos[1], l.pos[2] });
-			}
+			const std::vector<D3> pts = lightPoints(l);
 			std::vector<int> keep;
 			for (int r = 0; r < offsets.numFlatGeom; r++) {
 				const float4& pl = flatPolys[(size_t) FRAY_FLAT_POLY_VEC * r];
-				double behind = 1e300, scale = fabs((double) pl.w) + 1;
-				for (const D3& q: pts) {
-					behind = std::min(behind, pl.x * q.x + pl.y * q.y + pl.z * q.z - pl.w);
-					scale = std::max(scale, std::max(fabs(q.x), std::max(fabs(q.y), fabs(q.z))));
-				}
-				if (behind < 1e-4 * scale) keep.push_back(r); // the whole light is clearly in front otherwise
+				if (lightBehind(D3{ pl.x, pl.y, pl.z }, pl.w, pts)) keep.push_back(r);
 			}
 			if ((int) keep.size() == offsets.numFlatGeom || (int) keep.size() > shadowRoom) continue; // nothing gained / no room
 			shadowRoom -= (int) keep.size();
@@ -354,9 +510,38 @@ template <typename R> struct SceneImage {
 		offsets.numFlatSpheres = (int) spheres.size();
 		flatPolys.insert(flatPolys.end(), spheres.begin(), spheres.end());
 		flatInfo.insert(flatInfo.end(), sphereInfo.begin(), sphereInfo.end());
+		// convex hexahedra: header + six planes each (real faces first, then caps, unused slots repeat plane 0)
+		offsets.numFlatHex = (int) hexes.size();
+		for (int l = 0; l < FRAY_SHADOW_LIGHTS; l++) offsets.shadowHex[l] = 0xffffffffu;
+		for (size_t k = 0; k < hexes.size(); k++) {
+			const Hex& hx = hexes[k];
+			int4 hd;
+			hd.x = (int) flatInfo.size();
+			hd.y = (int) hx.faces.size();
+			hd.z = hd.w = 0;
+			float4 raw;
+			memcpy(&raw, &hd, sizeof(raw));
+			flatPolys.push_back(raw);
+			std::vector<float4> planes;
+			for (int c: hx.faces) {
+				planes.push_back(cands[c].rec[0]);
+				flatInfo.push_back(cands[c].fi);
+			}
+			for (const auto& cp: hx.caps) planes.push_back(plane4(cp.first, cp.second));
+			while ((int) planes.size() < FRAY_HEX_PLANES) planes.push_back(planes[0]);
+			flatPolys.insert(flatPolys.end(), planes.begin(), planes.end());
+			for (int li = 0; li < s.num_lights && li < FRAY_SHADOW_LIGHTS; li++) {
+				bool can = false;
+				const std::vector<D3> pts = lightPoints(s.lights[li]);
+				for (int c: hx.faces) can = can || lightBehind(cands[c].Nu, cands[c].d, pts);
+				if (!can) offsets.shadowHex[li] &= ~(1u << k);
+			}
+			feat |= FRAY_F_HEX;
+		}
+		offsets.numFlatInfo = (int) flatInfo.size();
 		if (getenv("FRAY_GPU_VERBOSE")) {
-			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records, %d spheres", offsets.numFlatGeom, offsets.numFlatAll - offsets.numFlatGeom,
-			        offsets.numFlatSpheres);
+			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records, %d spheres, %d convex hexahedra", offsets.numFlatGeom,
+			        offsets.numFlatAll - offsets.numFlatGeom, offsets.numFlatSpheres, offsets.numFlatHex);
 			for (int l = 0; l < s.num_lights && l < FRAY_SHADOW_LIGHTS; l++)
 				if (offsets.shadowCount[l] >= 0) fprintf(stderr, ", shadow set of light %d: %d", l, offsets.shadowCount[l]);
 			fprintf(stderr, "\n");

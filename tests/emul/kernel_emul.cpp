@@ -72,6 +72,7 @@ static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out
 	ft.polys = sc.flatPolys;
 	ft.info = sc.flatInfo;
 	ft.spheres = sc.flatPolys + FRAY_FLAT_POLY_VEC * sc.numFlatTotal;
+	ft.hexes = ft.spheres + sc.numFlatSpheres;
 	const int need = img.features;
 	auto run = [&]() { // the same variant selection as VariantDispatch in render_kernels.cuh
 		if (Variants<R>::count > 0 && (need & ~Variants<R>::mask(0)) == 0) renderRows<R, Variants<R>::mask(0)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
