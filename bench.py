@@ -34,7 +34,7 @@ UNIT = "Mrays/s"
 # 6.45 triangle tests, 0.54 light tests, 0.46 light samples, 0.86 hemisphere samples, 0.36 BRDF evals per ray
 FLOP_PER_RAY = 937.0
 BYTES_PER_RAY = 1430.0
-NCU_DRAM_BYTES_PER_LAUNCH = 213248 + 63232
+NCU_DRAM_BYTES_PER_LAUNCH = 44544 + 121856
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x FP32 lanes x 2 (FMA) x max SM clock
 
 
@@ -287,11 +287,11 @@ def main():
         roofline = {
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the ncu --set full
-            # capture profiles/r01_v6_cornell256_ncu_summary.txt (213 KB read + 63 KB written): the scene and the frame stay in L2
+            # capture profiles/r01_v12_cornell256_ncu_summary.txt (45 KB read + 122 KB written): the scene and the frame stay in L2
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.spp == SPP and world == 1 and precision == fb.FP32) else None,
             "peak_source": "FFMA micro-benchmark run in this process (fray_gpu_measure_peaks); MEASURED_PEAKS.json holds no FP32 figure",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
-            "kernel": "renderKernel<float, GI, FRAY_F_FLAT>" if precision == fb.FP32 else "renderKernel<double, GI, FRAY_F_GENERIC>",
+            "kernel": "renderKernel<float, GI, FRAY_F_FLAT|FRAY_F_HEX>" if precision == fb.FP32 else "renderKernel<double, GI, FRAY_F_GENERIC>",
             "kernel_ms_per_launch": kernel_ms_per_launch, "algorithmic_flop_per_ray": FLOP_PER_RAY, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
             "table_reads": {"algorithmic_gbs": rays_step * BYTES_PER_RAY / (kernel_ms_per_launch * 1e-3) / 1e9, "l2_peak_gbs": l2_peak,
                             "note": "the reference's per-ray table reads (node, box, triangle records); this kernel stages them once per CTA in shared "
