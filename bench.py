@@ -225,7 +225,11 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    barrier()  # after the sampler's start-up delay on rank 0, so that all ranks enter the timed region together
+    # the GPU idled while the sampler started (rank 0) or while waiting for rank 0 (others): one more untimed frame brings
+    # clocks and the NCCL channels back up, then all ranks enter the timed region together
+    barrier()
+    r.render_device()
+    barrier()
     t0 = time.time()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # evict L2 between timed frames (not timed)
