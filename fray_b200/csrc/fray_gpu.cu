@@ -284,6 +284,9 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	p.taskStride = bcount;
 	p.taskOffset = brank;
 	p.totalItems = (unsigned) ownedTiles * 32u * (unsigned) p.numChunks;
+	p.invTilesX = 1.0f / (float) tilesX;
+	p.invNumChunks = 1.0f / (float) p.numChunks;
+	p.exactDiv = ((double) totalTiles >= 4e6 || (double) ownedTiles * p.numChunks >= 4e6) ? 1 : 0; // beyond 2^22: integer division
 	p.out = dOut;
 	p.counters = c->dCounters;
 	p.workCounter = c->dWork;

@@ -35,6 +35,8 @@ struct RenderParams {
 	int chunk;        // C: samples per work item
 	int numChunks;    // ceil((s1 - s0) / C)
 	int tilesX;       // tiles per image row
+	float invTilesX, invNumChunks; // reciprocals for divmodSmall
+	int exactDiv;     // ranges too large for the float estimate: use integer division
 	int numOwnedTiles;
 	int taskStride, taskOffset; // owned tile j is tile j * taskStride + taskOffset of the frame
 	unsigned int totalItems;    // numOwnedTiles * 32 * numChunks
@@ -45,13 +47,31 @@ struct RenderParams {
 	int* errorFlag;
 };
 
+// x / d and x % d for x < 2^22 without the ~25-instruction integer division: float reciprocal estimate (off by at most one
+// in that range) and one correction step. The hosts sets invd = 1 / d and falls back to exact division for larger ranges.
+__device__ __forceinline__ void divmodSmall(unsigned x, unsigned d, float invd, bool exact, unsigned& q, unsigned& r)
+{
+	if (exact) {
+		q = x / d;
+		r = x - q * d;
+		return;
+	}
+	q = (unsigned) (__uint2float_rz(x) * invd);
+	int rem = (int) (x - q * d);
+	if (rem < 0) { q--; rem += (int) d; }
+	else if (rem >= (int) d) { q++; rem -= (int) d; }
+	r = (unsigned) rem;
+}
+
 // owned pixel slot (owned tile j, position in tile) -> pixel; false outside the image (border tiles)
 __device__ __forceinline__ bool slotPixel(const RenderParams& p, unsigned slot, int& px, int& py)
 {
 	const unsigned j = slot >> 5, within = slot & 31u;
 	const unsigned t = j * (unsigned) p.taskStride + (unsigned) p.taskOffset;
-	px = (int) (t % (unsigned) p.tilesX) * FRAY_TILE_W + (int) (within % FRAY_TILE_W);
-	py = (int) (t / (unsigned) p.tilesX) * FRAY_TILE_H + (int) (within / FRAY_TILE_W);
+	unsigned ty, tx;
+	divmodSmall(t, (unsigned) p.tilesX, p.invTilesX, p.exactDiv != 0, ty, tx);
+	px = (int) tx * FRAY_TILE_W + (int) (within % FRAY_TILE_W);
+	py = (int) ty * FRAY_TILE_H + (int) (within / FRAY_TILE_W);
 	return px < p.width && py < p.height;
 }
 
@@ -137,7 +157,8 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 				const unsigned id = poolNext + rank;
 				// id = (ownedTile * numChunks + chunk) * 32 + within
 				const unsigned within = id & 31u, tc = id >> 5;
-				const unsigned chunk = tc % (unsigned) p.numChunks, j = tc / (unsigned) p.numChunks;
+				unsigned chunk, j;
+				divmodSmall(tc, (unsigned) p.numChunks, p.invNumChunks, p.exactDiv != 0, j, chunk);
 				const unsigned slot = (j << 5) | within;
 				if (slotPixel(p, slot, px, py)) {
 					hasItem = true;
