@@ -796,14 +796,15 @@ template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
 // The kernel variants compiled per precision, smallest first; a scene runs on the first one that covers its feature bits.
 template <typename R> struct Variants;
 template <> struct Variants<float> {
-	static constexpr int count = 5;
+	static constexpr int count = 6;
 	static constexpr int kLean = FRAY_F_FLAT | FRAY_F_HEX;
 	static constexpr int mask(int i)
 	{
 		return i == 0 ? kLean                                                      // brute-force meshes, planes, lights (cornell_box)
 		     : i == 1 ? (kLean | FRAY_F_SPHERES)                                     // + translated spheres (smallpt)
-		     : i == 2 ? (kLean | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
-		     : i == 3 ? (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX) // everything but CSG
+		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_TEX)                     // textured brute-force meshes and planes (zaphod)
+		     : i == 3 ? (kLean | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
+		     : i == 4 ? (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX) // everything but CSG
 		              : (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
 	}
 };
@@ -1128,7 +1129,7 @@ FRAY_HD void lightSample(const DLight<R>& l, RNG& rng, int sampleIdx, const V3<R
 // Whitted shading: local terms (Lambert / Phong), src/shading.cpp:48-80, 101-144
 // ---------------------------------------------------------------------------------------------------
 template <typename R, int F, typename RNG>
-FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
+FRAY_HD Col shadeDirectBody(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
 {
 	Col diffuse = loadCol(s.color);
 	if ((F & FRAY_F_TEX) && s.texture >= 0) diffuse = diffuse * sampleTexture(sc, s.texture, rayDir, h.norm, h.u, h.v);
@@ -1164,6 +1165,16 @@ FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShad
 		result = result + sum / (float) ns;
 	}
 	return result;
+}
+
+// One out-of-line copy for the nested levels of Layered shaders (and for the whole parity unit, where compile time matters
+// more than speed). The node's own shader (level 0) gets the body inlined in the fast-precision kernels: behind a call the
+// scene and the shared-memory tables are reached through generic pointers (LD + R2UR instead of LDS / LDC), and with 32
+// shadow rays per hit in data/boxed.fray this function is the Whitted hot loop.
+template <typename R, int F, typename RNG>
+FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
+{
+	return shadeDirectBody<R, F>(sc, ft, s, rayDir, h, rng, cnt);
 }
 
 // refract(), src/vector.h:184-191; returns false on total internal reflection
@@ -1223,7 +1234,10 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 	switch (s.type) {
 		case FRAY_SHADER_CONST: accum = accum + weight * loadCol(s.color); return; // src/shading.cpp:35-38
 		case FRAY_SHADER_LAMBERT:
-		case FRAY_SHADER_PHONG: accum = accum + weight * shadeDirect<R, F>(sc, ft, s, rayDir, h, rng, cnt); return;
+		case FRAY_SHADER_PHONG:
+			if (LEVEL == 0 && !Num<R>::kExact) accum = accum + weight * shadeDirectBody<R, F>(sc, ft, s, rayDir, h, rng, cnt);
+			else accum = accum + weight * shadeDirect<R, F>(sc, ft, s, rayDir, h, rng, cnt);
+			return;
 		case FRAY_SHADER_REFL: {
 			const V3<R> n = faceforward(rayDir, h.norm);
 			const V3<R> start = h.ip + n * Num<R>::offsetEps(maxAbs(h.ip));

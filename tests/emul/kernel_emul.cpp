@@ -79,7 +79,8 @@ static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out
 		else if (Variants<R>::count > 1 && (need & ~Variants<R>::mask(1)) == 0) renderRows<R, Variants<R>::mask(1)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 		else if (Variants<R>::count > 2 && (need & ~Variants<R>::mask(2)) == 0) renderRows<R, Variants<R>::mask(2)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 		else if (Variants<R>::count > 3 && (need & ~Variants<R>::mask(3)) == 0) renderRows<R, Variants<R>::mask(3)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
-		else renderRows<R, Variants<R>::mask(4)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else if (Variants<R>::count > 4 && (need & ~Variants<R>::mask(4)) == 0) renderRows<R, Variants<R>::mask(4)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
+		else renderRows<R, Variants<R>::mask(5)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);
 	};
 	for (int t = 1; t < threads; t++) pool.emplace_back(run);
 	run();
