@@ -1172,8 +1172,10 @@ FRAY_HD Col shadeDirectBody(const DScene<R>& sc, const FlatTab& ft, const DShade
 // scene and the shared-memory tables are reached through generic pointers (LD + R2UR instead of LDS / LDC), and with 32
 // shadow rays per hit in data/boxed.fray this function is the Whitted hot loop.
 template <typename R, int F, typename RNG>
-FRAY_HD_COLD Col shadeDirect(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
+FRAY_HD_COLD Col shadeDirect(const DScene<R> sc, const FlatTab ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
 {
+	// `sc` BY VALUE: a reference would force the caller to keep the kernel's parameter block addressable, i.e. in local
+	// memory, and every table pointer of the whole kernel would then be loaded from there and dereferenced generically
 	return shadeDirectBody<R, F>(sc, ft, s, rayDir, h, rng, cnt);
 }
 
