@@ -21,7 +21,7 @@
 //     edge_i = (m_i, c_i)      inside  <=>  m_i.p + c_i >= 0 for i = 0..3  (for a triangle these are the barycentrics
 //                                                                               lambda2, lambda3, 1-lambda2-lambda3 and 1)
 // The kernels stage the table in shared memory once per CTA; the loop below is branch-free, every lane of a warp walks the
-// same records (128-bit broadcast reads), and a ray costs ~40 issue slots per record whatever the other lanes do.
+// same records (128-bit broadcast reads), and a ray costs 36 issue slots per record whatever the other lanes do.
 // Attributes of the winning record (node, triangle ids, world shading normal) are looked up afterwards in FlatInfo.
 #pragma once
 #include <stdint.h>

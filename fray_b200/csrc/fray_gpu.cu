@@ -1,6 +1,6 @@
 // fray_gpu.cu -- context management and the C ABI of libfray_gpu.so (include/fray_gpu.h).
 //
-// The context owns every device allocation: the scene image (one blob, see scene_image.h), the bucket list of the
+// The context owns every device allocation: the scene image (one blob, see scene_image.h), the chunk-sum scratch buffer of the
 // current call, the work counter / ray counters, a device framebuffer and a pinned host staging buffer for
 // fray_gpu_render(). One CUDA stream per context; kernel time is measured with CUDA events on that stream.
 // There is no CPU code path: if CUDA is unavailable every entry point fails with FRAY_GPU_ENODEVICE.

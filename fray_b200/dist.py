@@ -4,7 +4,7 @@ The reference distributes 48x48 buckets to threads through an atomic cursor (/ro
 src/sdl.cpp:243-262) and every thread writes its own pixels of the shared `vfb`. Across GPUs the same decomposition is
 static and needs exactly one collective at the end of the frame:
 
-* ``tiles``   -- rank r owns the buckets b of the serpentine list with b % world == r, renders all samples of them and
+* ``tiles``   -- rank r owns the 8x4 pixel tiles t of the frame with t % world == r, renders all samples of them and
                  leaves zeros elsewhere; the partial frames are summed onto rank 0 (``reduce(SUM)``; disjoint pixels, so
                  the sum is exact) and divided by spp there.
 * ``samples`` -- rank r renders samples [r*spp/world, (r+1)*spp/world) of EVERY pixel (possible because the counter-based
