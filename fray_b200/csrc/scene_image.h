@@ -72,6 +72,18 @@ template <typename R> struct SceneImage {
 			}
 		return false;
 	}
+	static bool shaderUsesTexture(const FrayGpuScene& s, int si, int depth)
+	{
+		if (si < 0 || depth > 8) return false;
+		const FrayGpuShader& sh = s.shaders[si];
+		if (sh.texture >= 0) return true;
+		if (sh.type == FRAY_SHADER_LAYERED)
+			for (int i = 0; i < sh.num_layers; i++) {
+				const FrayGpuLayer& L = s.layers[sh.first_layer + i];
+				if (L.texture >= 0 || shaderUsesTexture(s, L.shader, depth + 1)) return true;
+			}
+		return false;
+	}
 	static int layeredDepth(const FrayGpuScene& s, int si, int depth)
 	{
 		if (depth > 8) return 99;
@@ -744,7 +756,11 @@ template <typename R> struct SceneImage {
 			o.pad[0] = o.pad[1] = o.pad[2] = 0;
 		}
 		// feature bits this scene needs from the kernels
-		if (s.num_textures > 0 || s.has_environment) features |= FRAY_F_TEX;
+		// textures count only if something that is rendered refers to one (smallpt.fray defines a Fresnel texture and a Layered
+		// shader that no node uses)
+		if (s.has_environment) features |= FRAY_F_TEX;
+		for (int i = 0; i < s.num_nodes; i++)
+			if (shaderUsesTexture(s, s.nodes[i].shader, 0)) features |= FRAY_F_TEX;
 		for (int i = 0; i < s.num_nodes; i++)
 			if (s.nodes[i].bump >= 0) features |= FRAY_F_TEX;
 		if (!Num<R>::kExact) features |= buildFlat(s, nodes);
