@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 	int cur = 0, end = 0;  // next sample / end of the chunk
 	Col accum(0, 0, 0);    // sum over the finished samples of the chunk
 	Col eyeCol(0, 0, 0);   // radiance of the path / ray tree in flight
-	RngT<(GI && F == Variants<float>::kLean)> rng; // stream of the sample in flight (branch 0)
+	RngT<(GI && (F == Variants<float>::kLean || F == (Variants<float>::kLean | FRAY_F_SPHERES)))> rng; // stream of the sample in flight (branch 0)
 	PathState<R> ps;
 	Ray<R> rightEye;       // stereo: the second ray is generated up front (src/main.cpp:307-308) and traced afterwards
 	int eye = 0;
