@@ -172,7 +172,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="paths per pixel (the headline config is 256)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
-    ap.add_argument("--split", default="tiles", choices=["tiles", "samples", "auto"], help="multi-GPU decomposition (BASELINE.json: tiles for cornell)")
+    ap.add_argument("--split", default="tiles", choices=["tiles", "p2p", "samples", "auto"],
+                    help="multi-GPU decomposition: tiles (BASELINE.json for cornell; NCCL reduce), p2p (tiles written straight into rank 0's frame), samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -239,7 +240,7 @@ def main():
         st = r.stats()  # syncs; per-step kernel time + ray counters of this rank
         kernel_ms.append(st.device_ms)
         rays_step = st.rays
-        launches_step = st.kernel_launches + (1 if rank == 0 else 0)  # render (+ combine) kernels, and the resolve kernel on rank 0
+        launches_step = st.kernel_launches + (1 if (rank == 0 and r.mode != "p2p") else 0)  # render (+ combine), and resolve on rank 0
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None

@@ -26,6 +26,7 @@ FP64 = 1
 RENDER_BEAUTY = 0
 RENDER_AOV = 1
 FRAME_SUM = 1
+FRAME_OWNED_ONLY = 2
 
 
 class FraySettings(C.Structure):  # FrayGpuSettings
@@ -129,6 +130,9 @@ def gpu_lib() -> C.CDLL:
         L.fray_gpu_render.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.POINTER(FrayStats)]
         L.fray_gpu_render_device.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.c_void_p]
         L.fray_gpu_resolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.fray_gpu_frame_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_char_p]
+        L.fray_gpu_frame_import.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.fray_gpu_frame_close.argtypes = [C.c_void_p, C.c_void_p]
         L.fray_gpu_sync.argtypes = [C.c_void_p, C.POINTER(FrayStats)]
         L.fray_gpu_destroy.argtypes = [C.c_void_p]
         L.fray_gpu_measure_peaks.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -247,6 +251,22 @@ class GpuContext:
 
     def resolve_device(self, d_sum: int, d_rgb: int, spp: int, stream: int = 0):
         self._check(self._lib.fray_gpu_resolve_device(self._ctx, d_sum, d_rgb, spp, stream), "fray_gpu_resolve_device")
+
+    def frame_export(self) -> tuple[int, bytes]:
+        """(device address, 64-byte IPC handle) of a context-owned frame other processes can map (fray_gpu_frame_export)."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self._lib.fray_gpu_frame_export(self._ctx, C.byref(ptr), handle), "fray_gpu_frame_export")
+        return int(ptr.value), handle.raw
+
+    def frame_import(self, handle: bytes) -> int:
+        """Map a frame exported by another process's context on another GPU of this node; returns the device address."""
+        ptr = C.c_void_p()
+        self._check(self._lib.fray_gpu_frame_import(self._ctx, handle, C.byref(ptr)), "fray_gpu_frame_import")
+        return int(ptr.value)
+
+    def frame_close(self, d_frame: int):
+        self._check(self._lib.fray_gpu_frame_close(self._ctx, d_frame), "fray_gpu_frame_close")
 
     def sync(self) -> RenderStats:
         stats = FrayStats()

@@ -51,6 +51,7 @@ struct FrayGpuCtx {
 	unsigned long long* dCounters = nullptr; // 3 counters
 	unsigned int* dWork = nullptr;
 	int* dError = nullptr;
+	float* dShared = nullptr;    // frame exported to other processes (fray_gpu_frame_export)
 	float* dFrame = nullptr;     // own framebuffer for fray_gpu_render
 	float* hStaging = nullptr;   // pinned
 	int occGI = -1, occWhitted = -1;
@@ -147,6 +148,7 @@ void fray_gpu_destroy(FrayGpuCtx* c)
 	cudaFree(c->dWork);
 	cudaFree(c->dError);
 	cudaFree(c->dFrame);
+	cudaFree(c->dShared);
 	if (c->hStaging) cudaFreeHost(c->hStaging);
 	if (c->evStart) cudaEventDestroy(c->evStart);
 	if (c->evStop) cudaEventDestroy(c->evStop);
@@ -303,7 +305,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 		p.scratch = c->dScratch;
 	}
 
-	if (bcount > 1) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
+	if (bcount > 1 && !(f->flags & FRAY_FRAME_OWNED_ONLY)) CUDA_TRY(cudaMemsetAsync(dOut, 0, (size_t) c->width * c->height * 3 * sizeof(float), stream));
 	CUDA_TRY(cudaMemsetAsync(c->dCounters, 0, 3 * sizeof(unsigned long long), stream));
 	CUDA_TRY(cudaMemsetAsync(c->dWork, 0, sizeof(unsigned int), stream));
 
@@ -379,6 +381,43 @@ int fray_gpu_render_device(FrayGpuCtx* c, const FrayGpuFrame* frame, void* d_rgb
 {
 	if (!c) return fail(FRAY_GPU_EINVAL, "null argument");
 	return renderInto(c, frame, (float*) d_rgb, cuda_stream ? (cudaStream_t) cuda_stream : c->stream, true);
+}
+
+int fray_gpu_frame_export(FrayGpuCtx* c, void** d_frame, unsigned char handle[64])
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the IPC handle as 64 opaque bytes");
+	if (!c || !d_frame || !handle) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	if (!c->dShared) {
+		const size_t bytes = (size_t) c->width * c->height * 3 * sizeof(float);
+		CUDA_TRY(cudaMalloc(&c->dShared, bytes));
+		CUDA_TRY(cudaMemset(c->dShared, 0, bytes));
+	}
+	cudaIpcMemHandle_t h;
+	CUDA_TRY(cudaIpcGetMemHandle(&h, c->dShared));
+	memcpy(handle, &h, sizeof(h));
+	*d_frame = c->dShared;
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_frame_import(FrayGpuCtx* c, const unsigned char handle[64], void** d_frame)
+{
+	if (!c || !d_frame || !handle) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof(h));
+	void* p = nullptr;
+	CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	*d_frame = p;
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_frame_close(FrayGpuCtx* c, void* d_frame)
+{
+	if (!c || !d_frame) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	CUDA_TRY(cudaIpcCloseMemHandle(d_frame));
+	return FRAY_GPU_OK;
 }
 
 int fray_gpu_resolve_device(FrayGpuCtx* c, const void* d_sum, void* d_rgb, int32_t spp, void* cuda_stream)

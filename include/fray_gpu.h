@@ -256,6 +256,9 @@ enum {
 };
 
 #define FRAY_FRAME_SUM 1u   /* write per-pixel SUMS over the rendered samples instead of sum / spp */
+#define FRAY_FRAME_OWNED_ONLY 2u /* tile split: write only the pixels of this call's share and leave all others untouched (the
+                                 default clears them so that partial frames can be summed). For shares that write straight into
+                                 ONE frame, e.g. rank 0's frame mapped into every GPU through fray_gpu_frame_import(). */
 
 /* Samples per pixel by the reference's rule (src/main.cpp:395-400). */
 int fray_gpu_samples_per_pixel(const FrayGpuScene* scene);
@@ -301,6 +304,16 @@ int fray_gpu_render(FrayGpuCtx* ctx, const FrayGpuFrame* frame, float* rgb_out, 
  * written as 0 so that partial frames from several GPUs can be summed (ncclReduce). Stats are valid
  * after fray_gpu_sync(). */
 int fray_gpu_render_device(FrayGpuCtx* ctx, const FrayGpuFrame* frame, void* d_rgb, void* cuda_stream);
+
+/* Peer-to-peer frames (multi-GPU tile split without a reduction). fray_gpu_frame_export() allocates a frame of
+ * width*height*3 floats on the context's device (owned by the context) and returns its address and an opaque 64-byte handle
+ * (a cudaIpcMemHandle_t); another PROCESS that drives another GPU of the same node passes the handle to
+ * fray_gpu_frame_import() and gets an address through which its kernels write into that frame over NVLink (pass it as d_rgb to
+ * fray_gpu_render_device with FRAY_FRAME_OWNED_ONLY). The importer calls fray_gpu_frame_close() when done. The caller
+ * orders "all shares are written" before "the frame is read" (e.g. a barrier on the streams involved). */
+int fray_gpu_frame_export(FrayGpuCtx* ctx, void** d_frame, unsigned char handle[64]);
+int fray_gpu_frame_import(FrayGpuCtx* ctx, const unsigned char handle[64], void** d_frame);
+int fray_gpu_frame_close(FrayGpuCtx* ctx, void* d_frame);
 
 /* d_rgb[i] = d_sum[i] / spp on the device (the `avg / samplesPerPixel` of src/main.cpp:360). */
 int fray_gpu_resolve_device(FrayGpuCtx* ctx, const void* d_sum, void* d_rgb, int32_t spp, void* cuda_stream);

@@ -1,0 +1,50 @@
+#!/usr/bin/env python3
+"""Multi-GPU check (run under torchrun on >= 2 GPUs): the three decompositions of fray_b200.dist give the same frame.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_p2p.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import fray_b200 as fb
+import fray_b200.dist as fdist
+import oracle_util as ou
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    scene = fb.Scene(ou.override_scene("cornell_box", "p2pcheck", dict(frameWidth=200, frameHeight=152, pathsPerPixel=16)))
+    frames = {}
+    for mode in ("tiles", "p2p", "samples"):
+        r = fdist.DistributedRenderer(scene, mode=mode, device=local)
+        for _ in range(3):  # repeated frames: the peer frame is overwritten in place
+            out = r.render()
+        if rank == 0:
+            frames[mode] = (r.mode, out.copy())
+        dist.barrier()
+        r.close()
+    if rank == 0:
+        single = fb.GpuContext(scene, local, fb.FP32)
+        want, _ = single.render()
+        single.close()
+        for mode, (used, img) in frames.items():
+            d = np.abs(img - want).max()
+            print(f"{mode:8s} (ran as {used:7s}) max |difference| to the single-GPU frame: {d:.3e}")
+            assert d <= (1e-5 if mode == "samples" else 0.0) or (mode != "samples" and d < 1e-6), (mode, d)
+        print(f"check_p2p: OK on {world} GPUs")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
