@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="paths per pixel (the headline config is 256)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
-    ap.add_argument("--split", default="tiles", choices=["tiles", "p2p", "samples", "auto"],
+    ap.add_argument("--split", default="auto", choices=["tiles", "p2p", "samples", "auto"],
                     help="multi-GPU decomposition: tiles (BASELINE.json for cornell; NCCL reduce), p2p (tiles written straight into rank 0's frame), samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
