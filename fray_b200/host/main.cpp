@@ -8,8 +8,13 @@
 // include/fray_gpu.h -- loaded with dlopen so that the host layer has no link-time CUDA dependency. There is no CPU
 // renderer in this build: without --gpu (or without a CUDA device) the tool says so and fails.
 //
-//   fray --gpu [--fp64] [--out frame.bmp] [--seed N] [--spp N] [--device D] [--frames K]
+//   fray --gpu [--fp64] [--out frame.bmp] [--seed N] [--spp N] [--device D] [--frames K] [--move dx,dz,dyaw,dpitch]
 //        [--bucket-rank R --bucket-count C] [--samples A:B] [--aov] [-v] scene.fray
+//
+// --frames K --move ... is the headless form of the reference's interactive loop (mainloop, src/main.cpp:437-491): before
+// every frame after the first the camera is moved and turned by the given amounts (Camera::move / Camera::rotate,
+// src/camera.cpp:95-106), re-prepared with beginFrame() and sent to the GPU with fray_gpu_update_camera() -- no scene upload.
+// With several frames, "%d" in --out is replaced by the frame number.
 //
 // --bucket-* and --samples render one shard of the frame (tile split / sample split, include/fray_gpu.h FrayGpuFrame) so
 // that an outer launcher can spread a frame over several GPUs; fray_b200/dist.py does that with one process per GPU and an
@@ -35,6 +40,7 @@ struct GpuApi {
 	int (*device_count)(void) = nullptr;
 	int (*create)(const FrayGpuScene*, int, int, FrayGpuCtx**) = nullptr;
 	int (*render)(FrayGpuCtx*, const FrayGpuFrame*, float*, FrayGpuStats*) = nullptr;
+	int (*update_camera)(FrayGpuCtx*, const FrayGpuCamera*) = nullptr;
 	void (*destroy)(FrayGpuCtx*) = nullptr;
 	const char* (*last_error)(void) = nullptr;
 };
@@ -66,6 +72,7 @@ bool loadGpu(GpuApi& api, std::string& err)
 	FRAY_SYM(device_count, "fray_gpu_device_count");
 	FRAY_SYM(create, "fray_gpu_create");
 	FRAY_SYM(render, "fray_gpu_render");
+	FRAY_SYM(update_camera, "fray_gpu_update_camera");
 	FRAY_SYM(destroy, "fray_gpu_destroy");
 	FRAY_SYM(last_error, "fray_gpu_last_error");
 #undef FRAY_SYM
@@ -76,7 +83,7 @@ bool loadGpu(GpuApi& api, std::string& err)
 	return true;
 }
 
-void usage() { fprintf(stderr, "Usage: fray --gpu [--fp64] [--out file.bmp|.exr] [--seed N] [--spp N] [--device D] [--frames K]\n"
+void usage() { fprintf(stderr, "Usage: fray --gpu [--fp64] [--out file.bmp|.exr] [--seed N] [--spp N] [--device D] [--frames K] [--move dx,dz,dyaw,dpitch]\n"
                                "            [--bucket-rank R --bucket-count C] [--samples A:B] [--aov] [-v] scene.fray\n"); }
 
 } // namespace
@@ -88,6 +95,8 @@ int main(int argc, char** argv)
 	FrayGpuFrame frame;
 	memset(&frame, 0, sizeof(frame));
 	frame.seed = 42; // initRandom(42), src/main.cpp:502
+	double move[4] = { 0, 0, 0, 0 }; // per frame: dx, dz (Camera::move), dyaw, dpitch (Camera::rotate)
+	bool moving = false;
 	std::string out, sceneFile = "data/boxed.fray"; // default scene of the reference, src/main.cpp:51
 	for (int i = 1; i < argc; i++) {
 		const std::string a = argv[i];
@@ -104,6 +113,10 @@ int main(int argc, char** argv)
 		else if (a == "--spp") frame.spp = atoi(next("--spp"));
 		else if (a == "--device") device = atoi(next("--device"));
 		else if (a == "--frames") frames = atoi(next("--frames"));
+		else if (a == "--move") {
+			if (sscanf(next("--move"), "%lf,%lf,%lf,%lf", &move[0], &move[1], &move[2], &move[3]) != 4) { usage(); return -1; }
+			moving = true;
+		}
 		else if (a == "--bucket-rank") frame.bucket_rank = atoi(next("--bucket-rank"));
 		else if (a == "--bucket-count") frame.bucket_count = atoi(next("--bucket-count"));
 		else if (a == "--samples") {
@@ -144,7 +157,16 @@ int main(int argc, char** argv)
 	std::vector<float> rgb((size_t) W * H * 3);
 	FrayGpuStats stats;
 	memset(&stats, 0, sizeof(stats));
+	int rc = 0;
 	for (int f = 0; f < frames; f++) {
+		if (f > 0 && moving) {
+			FrayGpuCamera cam;
+			if (fray_host_move_camera(scene, move[0], move[1], move[2], move[3], &cam) != 0 || api.update_camera(ctx, &cam) != FRAY_GPU_OK) {
+				fprintf(stderr, "fray: camera update failed: %s\n", api.last_error());
+				api.destroy(ctx);
+				return -5;
+			}
+		}
 		const auto t0 = std::chrono::steady_clock::now();
 		if (api.render(ctx, &frame, rgb.data(), &stats) != FRAY_GPU_OK) {
 			fprintf(stderr, "fray: %s\n", api.last_error());
@@ -157,11 +179,15 @@ int main(int argc, char** argv)
 			printf("  %dx%d, %llu rays (%llu primary, %llu shadow), device %.3f ms, %.1f Mrays/s\n", W, H, (unsigned long long) stats.rays,
 			       (unsigned long long) stats.primary_rays, (unsigned long long) stats.shadow_rays, stats.device_ms,
 			       stats.device_ms > 0 ? stats.rays / stats.device_ms / 1e3 : 0.0);
-	}
-	int rc = 0;
-	if (!out.empty() && fray_host_save_image(out.c_str(), rgb.data(), W, H) != 0) {
-		fprintf(stderr, "fray: cannot write %s: %s\n", out.c_str(), fray_host_last_error());
-		rc = -6;
+		if (!out.empty() && (f == frames - 1 || out.find("%d") != std::string::npos)) {
+			std::string name = out;
+			const size_t pos = name.find("%d");
+			if (pos != std::string::npos) name.replace(pos, 2, std::to_string(f));
+			if (fray_host_save_image(name.c_str(), rgb.data(), W, H) != 0) {
+				fprintf(stderr, "fray: cannot write %s: %s\n", name.c_str(), fray_host_last_error());
+				rc = -6;
+			}
+		}
 	}
 	api.destroy(ctx);
 	fray_host_free_scene(scene);

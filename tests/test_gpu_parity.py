@@ -207,4 +207,29 @@ def test_cli_renders_and_writes_bmp(tmp_path, data_dir):
     got = fb.load_image(out)
     assert got.shape == want.shape
     # 8-bit BMP: nearestInt(clamp01(x) * 255), src/color.h:29-34,59-66
-    np.testing.assert_allclose(got, np.round(np.clip(want, 0, 1) * 255) / 255, atol=1e-6)
+    np.testing.assert_allclose(got, np.floor(np.clip(want, 0, 1) * np.float32(255) + np.float32(0.5)) / 255, atol=1e-6)
+
+
+def test_cli_frame_loop_with_camera_moves(tmp_path, data_dir):
+    """`fray --gpu --frames 3 --move ...`: the headless interactive loop (mainloop, src/main.cpp:437-491) -- the camera moves
+    between frames through fray_gpu_update_camera, the scene is uploaded once; frames match the library driven the same way."""
+    import subprocess
+    import fray_b200.build as fbuild
+    exe = fbuild.build_cli()
+    scene_file = ou.override_scene("forest", "cliloop", dict(frameWidth=96, frameHeight=64, interactive="off"))
+    pattern = str(tmp_path / "f%d.bmp")
+    r = subprocess.run([exe, "--gpu", "--fp64", "--frames", "3", "--move", "2,-1.5,8,-2", "--out", pattern, scene_file], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("Render took") == 3
+    sc = fb.Scene(scene_file)
+    ctx = fb.GpuContext(sc, 0, fb.FP64)
+    for f in range(3):
+        if f > 0:
+            ctx.update_camera(sc.move_camera(dx=2.0, dz=-1.5, dyaw=8.0, dpitch=-2.0))
+        want, _ = ctx.render(seed=42)
+        got = fb.load_image(str(tmp_path / f"f{f}.bmp"))
+        np.testing.assert_allclose(got, np.floor(np.clip(want, 0, 1) * np.float32(255) + np.float32(0.5)) / 255, atol=1e-6)
+        if f > 0:
+            assert not np.array_equal(got, prev)
+        prev = got
+    ctx.close()
