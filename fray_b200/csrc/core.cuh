@@ -206,6 +206,7 @@ template <typename R> struct DCamera {
 	R w, h, aperture, focalDist, stereoSep;
 	float leftMask[3], rightMask[3];
 	int dof;
+	R du[3], dv[3]; // (topRight - topLeft) / w and (bottomLeft - topLeft) / h: the per-pixel steps of the screen plane (fast precision)
 };
 
 template <typename R> struct DScene {
@@ -1531,7 +1532,8 @@ template <typename R> FRAY_HD Ray<R> screenRay(const DCamera<R>& c, R x, R y, in
 {
 	const V3<R> tl = load3(c.topLeft), tr = load3(c.topRight), bl = load3(c.bottomLeft);
 	Ray<R> r;
-	r.dir = normalized(tl + (tr - tl) * (x / c.w) + (bl - tl) * (y / c.h));
+	if (Num<R>::kExact) r.dir = normalized(tl + (tr - tl) * (x / c.w) + (bl - tl) * (y / c.h)); // src/camera.cpp:62-64, operation for operation
+	else r.dir = normalized(tl + load3(c.du) * x + load3(c.dv) * y);
 	r.start = load3(c.pos);
 	if (which == 1) r.start = r.start + load3(c.right) * -c.stereoSep;
 	else if (which == 2) r.start = r.start + load3(c.right) * c.stereoSep;

@@ -115,6 +115,10 @@ template <typename R> static void convertCamera(DCamera<R>& d, const FrayGpuCame
 		d.bottomLeft[i] = (R) cam.bottom_left[i]; d.front[i] = (R) cam.front[i]; d.up[i] = (R) cam.up[i]; d.right[i] = (R) cam.right[i];
 		d.leftMask[i] = cam.left_mask[i]; d.rightMask[i] = cam.right_mask[i];
 	}
+	for (int i = 0; i < 3; i++) {
+		d.du[i] = (R) ((cam.top_right[i] - cam.top_left[i]) / cam.w);
+		d.dv[i] = (R) ((cam.bottom_left[i] - cam.top_left[i]) / cam.h);
+	}
 	d.w = (R) cam.w; d.h = (R) cam.h; d.aperture = (R) cam.aperture_size; d.focalDist = (R) cam.focal_plane_dist;
 	d.stereoSep = (R) cam.stereo_separation; d.dof = cam.dof;
 }

@@ -579,6 +579,10 @@ template <typename R> struct SceneImage {
 		cvt3(d.cam.front, s.camera.front);
 		cvt3(d.cam.up, s.camera.up);
 		cvt3(d.cam.right, s.camera.right);
+		for (int i = 0; i < 3; i++) {
+			d.cam.du[i] = (R) ((s.camera.top_right[i] - s.camera.top_left[i]) / s.camera.w);
+			d.cam.dv[i] = (R) ((s.camera.bottom_left[i] - s.camera.top_left[i]) / s.camera.h);
+		}
 		d.cam.w = (R) s.camera.w;
 		d.cam.h = (R) s.camera.h;
 		d.cam.aperture = (R) s.camera.aperture_size;
