@@ -86,11 +86,11 @@ class ClockSampler:
 
 
 def bench_scene_file(spp: int, extra: dict | None = None) -> str:
-    import oracle_util as ou  # only for its scene-override helper and data directory
+    from fray_b200.scenes import override_scene
     st = dict(pathsPerPixel=spp)
     st.update(extra or {})
     tag = "bench_" + "_".join(f"{k}{v}" for k, v in sorted(st.items()))
-    return ou.override_scene(SCENE, tag, st)
+    return override_scene(SCENE, tag, st)
 
 
 def run_reference(args, rank: int, world: int):

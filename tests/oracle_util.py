@@ -2,7 +2,7 @@
 
 * ``oracle_render``      -- our FP64 restatement (oracle/libfray_oracle.so) on a flattened scene
 * ``reference_render``   -- the real reference code with the counter RNG (oracle/_ref/fray_ref_ctr)
-* ``override_scene``     -- write a variant of a bundled scene with changed GlobalSettings / Camera properties
+* ``override_scene``     -- re-exported from fray_b200.scenes (variants of bundled scenes)
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ import fray_b200 as fb
 ROOT = fb.REPO_ROOT
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
-DATA_DIR = os.environ.get("FRAY_DATA", os.path.join(REF_DIR, "data"))
+from fray_b200.scenes import DATA_DIR  # noqa: E402
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 REF_CTR = os.path.join(REF_DIR, "fray_ref_ctr")
 REF_BIN = os.path.join(REF_DIR, "fray_ref")
@@ -101,39 +101,7 @@ def have_reference() -> bool:
     return os.path.exists(REF_CTR) and os.path.isdir(DATA_DIR)
 
 
-def scene_path(name: str) -> str:
-    """'cornell_box' or 'hw9/dragon' -> path of the bundled .fray file in the data mirror."""
-    return os.path.join(DATA_DIR, name + ".fray")
-
-
-_BLOCK_RE = {"GlobalSettings": re.compile(r"^\s*GlobalSettings\b[^{]*\{", re.M), "Camera": re.compile(r"^\s*Camera\b[^{]*\{", re.M)}
-
-
-def override_scene(name: str, tag: str, settings: dict | None = None, camera: dict | None = None) -> str:
-    """Write `<name>__<tag>.fray` beside the original (asset paths are relative to the scene file,
-    /root/reference/src/scene.cpp:710-721) with the given properties put FIRST in the block, so they win
-    (ParsedBlockImpl::findProperty returns the first match, src/scene.cpp:112-122)."""
-    src = scene_path(name)
-    text = open(src).read()
-    for block, props in (("GlobalSettings", settings), ("Camera", camera)):
-        if not props:
-            continue
-        m = _BLOCK_RE[block].search(text)
-        if not m:
-            raise RuntimeError(f"{src} has no {block} block")
-        ins = "".join(f"\n\t{k} {v}" for k, v in props.items())
-        text = text[:m.end()] + ins + text[m.end():]
-    dst = os.path.join(os.path.dirname(src), f"{os.path.basename(name)}__{tag}.fray")
-    # several ranks of one torchrun job ask for the same file at the same time: never expose a half-written one
-    if os.path.exists(dst):
-        with open(dst) as f:
-            if f.read() == text:
-                return dst
-    tmp = f"{dst}.{os.getpid()}.tmp"
-    with open(tmp, "w") as f:
-        f.write(text)
-    os.replace(tmp, dst)
-    return dst
+from fray_b200.scenes import override_scene, scene_path  # noqa: E402,F401  (the scene helpers are product code)
 
 
 def reference_render(scene_file: str, seed: int = 42, threads: int = 0, aov: bool = False):

@@ -30,7 +30,7 @@ def main():
     import numpy as np
 
     import fray_b200 as fb
-    import oracle_util as ou
+    from fray_b200 import scenes
     from conftest import golden_scene
     import shutil
     cases = json.load(open(os.path.join(ROOT, "tests", "golden", "cases.json")))
@@ -44,7 +44,7 @@ def main():
         assert kw.get("mode", fb.RENDER_BEAUTY) != fb.RENDER_BEAUTY or np.isfinite(out).all()  # a miss has distance inf in the AOV
 
     scenes = [golden_scene(cases, name) for name in cases]
-    extra = os.path.join(ou.DATA_DIR, "flat_transforms__test.fray")
+    extra = os.path.join(scenes.DATA_DIR, "flat_transforms__test.fray")
     shutil.copyfile(os.path.join(ROOT, "tests", "scenes", "flat_transforms.fray"), extra)
     scenes.append((extra, 7))
     for path, seed in scenes:

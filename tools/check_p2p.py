@@ -8,14 +8,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import torch.distributed as dist
 
 import fray_b200 as fb
 import fray_b200.dist as fdist
-import oracle_util as ou
+from fray_b200 import scenes
 
 
 def main():
@@ -23,7 +22,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rank, world = dist.get_rank(), dist.get_world_size()
-    scene = fb.Scene(ou.override_scene("cornell_box", "p2pcheck", dict(frameWidth=200, frameHeight=152, pathsPerPixel=16)))
+    scene = fb.Scene(scenes.override_scene("cornell_box", "p2pcheck", dict(frameWidth=200, frameHeight=152, pathsPerPixel=16)))
     frames = {}
     for mode in ("tiles", "p2p", "samples"):
         r = fdist.DistributedRenderer(scene, mode=mode, device=local)

@@ -8,9 +8,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fray_b200 as fb
-import oracle_util as ou
+from fray_b200 import scenes
 
 
 def main():
@@ -21,7 +20,7 @@ def main():
     precision = fb.FP64 if "--fp64" in sys.argv else fb.FP32
     if name == "forest":
         settings.setdefault("interactive", "off")
-    sc = fb.Scene(ou.override_scene(name, "once", settings or None))
+    sc = fb.Scene(scenes.override_scene(name, "once", settings or None))
     ctx = fb.GpuContext(sc, 0, precision)
     for _ in range(frames):
         img, s = ctx.render()
