@@ -13,10 +13,15 @@ from fray_b200 import scenes
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = sys.argv[1:]
+    frames = 3
+    if "--frames" in argv:
+        i = argv.index("--frames")
+        frames = int(argv[i + 1])
+        del argv[i:i + 2]
+    args = [a for a in argv if not a.startswith("--")]
     name = args[0]
     settings = dict(a.split("=", 1) for a in args[1:])
-    frames = int(sys.argv[sys.argv.index("--frames") + 1]) if "--frames" in sys.argv else 3
     precision = fb.FP64 if "--fp64" in sys.argv else fb.FP32
     if name == "forest":
         settings.setdefault("interactive", "off")
