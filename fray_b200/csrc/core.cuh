@@ -792,21 +792,23 @@ template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
 #define FRAY_F_ATTR 16  // some flat record interpolates normals / uvs
 #define FRAY_F_SPHERES 32 // the flat table has a sphere list
 #define FRAY_F_HEX 64     // the flat table has convex hexahedra
-#define FRAY_F_GENERIC (FRAY_F_NODES | FRAY_F_TEX)
+#define FRAY_F_LENS 128   // the camera uses depth of field or stereo
+#define FRAY_F_GENERIC (FRAY_F_NODES | FRAY_F_TEX | FRAY_F_LENS)
 
 // The kernel variants compiled per precision, smallest first; a scene runs on the first one that covers its feature bits.
 template <typename R> struct Variants;
 template <> struct Variants<float> {
 	static constexpr int count = 6;
 	static constexpr int kLean = FRAY_F_FLAT | FRAY_F_HEX;
+	static constexpr int kAll = kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_LENS;
 	static constexpr int mask(int i)
 	{
 		return i == 0 ? kLean                                                      // brute-force meshes, planes, lights (cornell_box)
 		     : i == 1 ? (kLean | FRAY_F_SPHERES)                                     // + translated spheres (smallpt)
-		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_TEX)                     // textured brute-force meshes and planes (zaphod)
+		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_TEX | FRAY_F_LENS)       // textured brute-force meshes and planes, any camera (zaphod)
 		     : i == 3 ? (kLean | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
-		     : i == 4 ? (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX) // everything but CSG
-		              : (kLean | FRAY_F_SPHERES | FRAY_F_ATTR | FRAY_F_NODES | FRAY_F_TEX | FRAY_F_CSG);
+		     : i == 4 ? kAll                                                         // everything but CSG
+		              : (kAll | FRAY_F_CSG);
 	}
 };
 template <> struct Variants<double> {
@@ -979,7 +981,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 			}
 		}
 	}
-	if (!(F & FRAY_F_FLAT) || !sc.lightsInFlat) {
+	if (!(F & FRAY_F_FLAT) || ((F & FRAY_F_NODES) && !sc.lightsInFlat)) { // (lights outside the table force FRAY_F_NODES, scene_image.h)
 		for (int l = 0; l < sc.numLights; l++) {
 			R d;
 			if (intersectLight(sc.lights[l], ray, d) && d < best.dist) {
@@ -1554,9 +1556,10 @@ template <typename R, typename RNG> FRAY_HD Ray<R> dofRay(const DCamera<R>& c, R
 	return ray;
 }
 
-template <typename R, typename RNG> FRAY_HD Ray<R> cameraRay(const DCamera<R>& c, RNG& rng, R x, R y, int which) // getRay, src/main.cpp:296-302
+// getRay, src/main.cpp:296-302. `lens`: the kernel variant was compiled with FRAY_F_LENS (depth of field / stereo possible)
+template <typename R, typename RNG> FRAY_HD Ray<R> cameraRay(const DCamera<R>& c, RNG& rng, R x, R y, int which, bool lens)
 {
-	return c.dof ? dofRay(c, rng, x, y, which) : screenRay(c, x, y, which);
+	return (lens && c.dof) ? dofRay(c, rng, x, y, which) : screenRay(c, x, y, lens ? which : 0);
 }
 
 FRAY_HD Col adjustSaturation(const Col& c, float amount) // src/color.h:128-134
@@ -1590,10 +1593,10 @@ FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, 
 	sampleOffset(sc.cam.dof || sc.gi, sampleIdx, rng, ox, oy);
 	// x + offsetX is evaluated in float in the reference (int + float), then widened to double
 	const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);
-	const bool stereo = sc.cam.stereoSep > 0;
+	const bool stereo = (F & FRAY_F_LENS) && sc.cam.stereoSep > 0;
 	const int eyes = stereo ? 2 : 1;
 	Ray<R> rays[2];
-	for (int e = 0; e < eyes; e++) rays[e] = cameraRay(sc.cam, rng, fx, fy, stereo ? 1 + e : 0);
+	for (int e = 0; e < eyes; e++) rays[e] = cameraRay(sc.cam, rng, fx, fy, stereo ? 1 + e : 0, (F & FRAY_F_LENS) != 0);
 	Col total(0, 0, 0);
 	for (int e = 0; e < eyes; e++) {
 		cnt.primary++;

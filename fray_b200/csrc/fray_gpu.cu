@@ -227,6 +227,10 @@ int fray_gpu_update_camera(FrayGpuCtx* c, const FrayGpuCamera* cam)
 	if (!c || !cam) return fail(FRAY_GPU_EINVAL, "null argument");
 	// the camera travels as a kernel parameter (constant bank), so a per-frame update costs no device copy
 	if (c->precision == FRAY_GPU_FP32) convertCamera(c->sc32.cam, *cam); else convertCamera(c->sc64.cam, *cam);
+	if ((cam->dof || cam->stereo_separation > 0) && !(c->features & FRAY_F_LENS)) { // the new camera needs a kernel variant with a lens
+		c->features |= FRAY_F_LENS;
+		c->occGI = c->occWhitted = -1;
+	}
 	if ((int) cam->w != c->width || (int) cam->h != c->height) return fail(FRAY_GPU_EINVAL, "frame size cannot change without re-creating the context");
 	return FRAY_GPU_OK;
 }

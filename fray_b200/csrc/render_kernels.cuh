@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned ltMask = (1u << lane) - 1u;
 	const bool randomOffsets = sc.cam.dof || sc.gi;
-	const bool stereo = sc.cam.stereoSep > 0;
+	const bool stereo = (F & FRAY_F_LENS) && sc.cam.stereoSep > 0;
 
 	RayCounters cnt = { 0, 0, 0 };
 	WhittedState<R> ws; // only touched by the Whitted instantiation
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 			float ox, oy;
 			sampleOffset(randomOffsets, s, rng, ox, oy);
 			const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);
-			Ray<R> first = cameraRay(sc.cam, rng, fx, fy, stereo ? 1 : 0);
-			if (stereo) rightEye = cameraRay(sc.cam, rng, fx, fy, 2);
+			Ray<R> first = cameraRay(sc.cam, rng, fx, fy, stereo ? 1 : 0, (F & FRAY_F_LENS) != 0);
+			if (stereo) rightEye = cameraRay(sc.cam, rng, fx, fy, 2, true);
 			eye = 0;
 			eyeCol = Col(0, 0, 0);
 			cnt.primary++;

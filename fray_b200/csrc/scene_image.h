@@ -767,7 +767,11 @@ template <typename R> struct SceneImage {
 			if (shaderUsesTexture(s, s.nodes[i].shader, 0)) features |= FRAY_F_TEX;
 		for (int i = 0; i < s.num_nodes; i++)
 			if (s.nodes[i].bump >= 0) features |= FRAY_F_TEX;
-		if (!Num<R>::kExact) features |= buildFlat(s, nodes);
+		if (s.camera.dof || s.camera.stereo_separation > 0) features |= FRAY_F_LENS;
+		if (!Num<R>::kExact) {
+			features |= buildFlat(s, nodes);
+			if (!offsets.lightsInFlat) features |= FRAY_F_NODES; // the generic light loop is compiled with the generic node loop
+		}
 		for (int i = 0; i < s.num_nodes; i++)
 			if (!nodes[i].inFlat) features |= FRAY_F_NODES;
 		if (Num<R>::kExact) features |= FRAY_F_GENERIC;
