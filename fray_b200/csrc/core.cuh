@@ -1344,7 +1344,7 @@ FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, RNG& primary, Wh
 		// sample t.k of a glossy reflection: Reflection::shade, src/shading.cpp:176-200
 		const DShader<R>& s = sc.shaders[t.shader];
 		RNG child;
-		child.init(primary.seed, primary.pixel, primary.sample, rngChildBranch(t.branch, t.count, t.k0 + (uint32_t) t.k));
+		child.initBranch(primary, rngChildBranch(t.branch, t.count, t.k0 + (uint32_t) t.k));
 		V3<R> b, c;
 		orthonormalSystem(t.n, b, c);
 		V3<R> reflected;
@@ -1378,7 +1378,7 @@ FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, RNG& primary, Wh
 		whittedStep<R, F>(sc, ft, t, primary, ws, accum, cnt);
 	} else {
 		RNG child;
-		child.init(primary.seed, primary.pixel, primary.sample, t.branch);
+		child.initBranch(primary, t.branch);
 		child.skip(t.count);
 		whittedStep<R, F>(sc, ft, t, child, ws, accum, cnt);
 	}

@@ -276,6 +276,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	RenderParams p;
 	memset(&p, 0, sizeof(p));
 	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
+	philoxRoundKeys(p.seed, p.roundKeys);
 	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
 	// chunk size: every lane of the grid should see >= ~20 items (measured optimum for a 1.5 ms call: 2 paths per item), so that the drain at the end of the kernel (lanes running
 	// dry while the last items finish; an item of C paths takes C x ~35 us on a busy SM) is a few percent of the call even

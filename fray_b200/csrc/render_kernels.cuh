@@ -31,6 +31,7 @@ struct RenderParams {
 	int spp;          // samples per pixel of the whole frame (divisor)
 	int s0, s1;       // sample range rendered by this call
 	uint32_t seed;
+	uint32_t roundKeys[10]; // philoxRoundKeys(seed)
 	int sumOnly;      // FRAY_FRAME_SUM
 	int chunk;        // C: samples per work item
 	int numChunks;    // ceil((s1 - s0) / C)
@@ -122,7 +123,8 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 	int cur = 0, end = 0;  // next sample / end of the chunk
 	Col accum(0, 0, 0);    // sum over the finished samples of the chunk
 	Col eyeCol(0, 0, 0);   // radiance of the path / ray tree in flight
-	RngT<(GI && (F == Variants<float>::kLean || F == (Variants<float>::kLean | FRAY_F_SPHERES)))> rng; // stream of the sample in flight (branch 0)
+	RngT<FRAY_RNG_KEYED> rng; // stream of the sample in flight (branch 0)
+	rng.keys = p.roundKeys;
 	PathState<R> ps;
 	Ray<R> rightEye;       // stereo: the second ray is generated up front (src/main.cpp:307-308) and traced afterwards
 	int eye = 0;

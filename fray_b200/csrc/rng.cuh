@@ -86,20 +86,56 @@ FRAY_HD uint32_t rngChildBranch(uint32_t branch, uint32_t draws, uint32_t k)
 	return rngMix(branch ^ rngMix(draws * 0x9E3779B9u + k + 1u)) | 1u;
 }
 
-// OUTLINE: generate blocks through the out-of-line philoxBlock (the lean path-tracing kernel, whose hot loop has to fit the
-// instruction cache) instead of inlining the ten rounds at every use (everything else: the call costs ~4 % there)
-template <bool OUTLINE> struct RngT {
+// Ten rounds with the round keys read from a table (kernel parameters: a constant-bank operand of the LOP3, which saves
+// the nine key additions per block of the seed-based form). keys[i] = seed + i * 0x9E3779B9; the second key word is constant.
+FRAY_HD Philox4 philox4x32_10_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* keys)
+{
+	uint32_t k1 = 0x46524159u;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+	for (int round = 0; round < 10; round++) {
+		const uint32_t lo0 = 0xD2511F53u * c0, hi0 = mulhi32(0xD2511F53u, c0);
+		const uint32_t lo1 = 0xCD9E8D57u * c2, hi1 = mulhi32(0xCD9E8D57u, c2);
+		c0 = hi1 ^ c1 ^ keys[round];
+		c1 = lo1;
+		c2 = hi0 ^ c3 ^ k1;
+		c3 = lo0;
+		k1 += 0xBB67AE85u;
+	}
+	return Philox4{ c0, c1, c2, c3 };
+}
+
+FRAY_HD void philoxRoundKeys(uint32_t seed, uint32_t* keys)
+{
+	for (int i = 0; i < 10; i++) keys[i] = seed + (uint32_t) i * 0x9E3779B9u;
+}
+
+// How a stream generates its blocks: inline from the seed (host code, the Whitted kernels), through the out-of-line
+// philoxBlock (one copy of the ten rounds per kernel), or inline with a round-key table (the render kernels: `keys` points
+// at RenderParams::roundKeys, i.e. into the kernel's constant bank).
+enum { FRAY_RNG_INLINE = 0, FRAY_RNG_OUTLINE = 1, FRAY_RNG_KEYED = 2 };
+
+template <int MODE> struct RngT {
 	uint32_t seed, pixel, sample, branch;
 	uint32_t count; // draws consumed
 	Philox4 blk;    // block ((count - 1) >> 2) when count & 3
+	const uint32_t* keys = nullptr; // FRAY_RNG_KEYED only
 
 	FRAY_HD void init(uint32_t seed_, uint32_t pixel_, uint32_t sample_, uint32_t branch_)
 	{
 		seed = seed_; pixel = pixel_; sample = sample_; branch = branch_; count = 0;
 	}
+	// another stream of the same (seed, pixel, sample)
+	FRAY_HD void initBranch(const RngT& parent, uint32_t branch_)
+	{
+		init(parent.seed, parent.pixel, parent.sample, branch_);
+		keys = parent.keys;
+	}
 	FRAY_HD void refill()
 	{
-		if (OUTLINE) blk = philoxBlock(count >> 2, pixel, sample, branch, seed);
+		if (MODE == FRAY_RNG_OUTLINE) blk = philoxBlock(count >> 2, pixel, sample, branch, seed);
+		else if (MODE == FRAY_RNG_KEYED) blk = philox4x32_10_keyed(count >> 2, pixel, sample, branch, keys);
 		else blk = philox4x32_10(count >> 2, pixel, sample, branch, seed, 0x46524159u);
 	}
 	FRAY_HD uint32_t next()
@@ -137,6 +173,6 @@ template <bool OUTLINE> struct RngT {
 	}
 };
 
-typedef RngT<false> Rng;
+typedef RngT<FRAY_RNG_INLINE> Rng;
 
 } // namespace fray
