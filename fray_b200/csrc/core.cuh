@@ -1447,6 +1447,8 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 	const R eps = Num<R>::offsetEps(maxAbs(h.ip));
 	const bool lambert = s.type == FRAY_SHADER_LAMBERT;
 
+	// all draws of the segment: 4 skipped + 4 for the light sample + 4 for the new direction (Lambert), 4 otherwise
+	rng.ensure(lambert ? 12 : 4);
 	// the first, discarded spawnRay (src/main.cpp:219-224) only advances the stream (4 draws for Lambert)
 	if (lambert) rng.skip(4);
 

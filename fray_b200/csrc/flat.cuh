@@ -164,7 +164,9 @@ FRAY_HD bool flatSpheresAny(const float4* __restrict__ S, int n, float ox, float
 // edge tests, no cracks along the edges. Equivalent to Triangle::intersectFast (src/triangle.cpp:66-94) with back-face
 // culling (src/mesh.cpp:106) over the faces, except on rays that pass exactly through an edge.
 #define FRAY_HEX_PLANES 6
-#define FRAY_HEX_VEC 7 // header {first FlatInfo index, number of real faces, -, -} + six planes (unused slots repeat plane 0)
+#define FRAY_HEX_VEC 7 // header {first FlatInfo index, number of real faces, cap mask of slots 4 and 5, -} + six planes: real faces, then
+                       // repeats of plane 0, caps (at most two) in the last slots
+#define FRAY_HEX_MAX_CAPS 2
 #define FRAY_MAX_HEX 16
 
 FRAY_HD bool flatHexTest(const float4* __restrict__ planes, float ox, float oy, float oz, float dx, float dy, float dz, float& tHit, int& jHit)
@@ -204,15 +206,39 @@ FRAY_HD void flatHexClosest(const float4* __restrict__ H, int n, float ox, float
 	}
 }
 
+// Any-hit form: no face index is needed, only "does the segment [0, tMax) enter the solid through a real face". The entry
+// parameter is the maximum over the front-facing planes, the exit the minimum over the back-facing ones (a select per plane
+// and FMNMX3 chains instead of the compare / select / select of the closest-hit form). Caps sit in the LAST slots (4 and 5, at
+// most two, header .z = bit mask): a front-facing cap bounds the entry from below -- entering through a cap is no hit.
+FRAY_HD bool flatHexAnyTest(const float4* __restrict__ planes, bool cap4, bool cap5, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
+{
+	const float inf = 3.0e38f;
+	float tIn[FRAY_HEX_PLANES], tOut[FRAY_HEX_PLANES];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+	for (int j = 0; j < FRAY_HEX_PLANES; j++) {
+		const float4 pl = planes[j];
+		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, fmaf(pl.z, dz, 0.0f))); // +0 seed: see flatHexTest
+		const float h = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
+		const float t = flatDivide(h, s);
+		const bool front = s < 0.0f;
+		tIn[j] = front ? t : -inf;
+		tOut[j] = front ? inf : t;
+	}
+	const float tLow = fmaxf(cap4 ? tIn[4] : -inf, cap5 ? tIn[5] : -inf);
+	const float tHit = fmaxf(fmaxf(fmaxf(tIn[0], tIn[1]), fmaxf(tIn[2], tIn[3])), fmaxf(cap4 ? -inf : tIn[4], cap5 ? -inf : tIn[5]));
+	const float tBound = fminf(fminf(fminf(tOut[0], tOut[1]), fminf(tOut[2], tOut[3])), fminf(tOut[4], tOut[5]));
+	return (tHit <= tBound) & (tHit >= 0.0f) & (tHit >= tLow) & (tHit < tMax);
+}
+
 FRAY_HD bool flatHexAny(const float4* __restrict__ H, int n, unsigned mask, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
 {
 	bool hit = false;
 	for (int i = 0; i < n; i++) {
 		if (!((mask >> i) & 1u)) continue;
 		const int4 hd = *reinterpret_cast<const int4*>(H + FRAY_HEX_VEC * i);
-		float t;
-		int j;
-		hit |= flatHexTest(H + FRAY_HEX_VEC * i + 1, ox, oy, oz, dx, dy, dz, t, j) & (j < hd.y) & (t < tMax);
+		hit |= flatHexAnyTest(H + FRAY_HEX_VEC * i + 1, (hd.z & 1) != 0, (hd.z & 2) != 0, ox, oy, oz, dx, dy, dz, tMax);
 	}
 	return hit;
 }

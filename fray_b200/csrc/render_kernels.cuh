@@ -98,6 +98,18 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 	return ft;
 }
 
+template <bool GI> struct RenderRng {
+	typedef RngT<FRAY_RNG_KEYED> type;
+	static __device__ __forceinline__ void attach(type& rng, uint32_t*, const uint32_t* keys) { rng.keys = keys; }
+};
+template <> struct RenderRng<true> {
+	typedef RngRing type;
+	static __device__ __forceinline__ void attach(type& rng, uint32_t* ring, const uint32_t* keys)
+	{
+		rng.attach((uint32_t) __cvta_generic_to_shared(ring + threadIdx.x), keys);
+	}
+};
+
 template <typename R, bool GI, int F>
 __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 : (Num<R>::kExact ? 1 : (GI ? 6 : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
@@ -123,8 +135,11 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 	int cur = 0, end = 0;  // next sample / end of the chunk
 	Col accum(0, 0, 0);    // sum over the finished samples of the chunk
 	Col eyeCol(0, 0, 0);   // radiance of the path / ray tree in flight
-	RngT<FRAY_RNG_KEYED> rng; // stream of the sample in flight (branch 0)
-	rng.keys = p.roundKeys;
+	// stream of the sample in flight (branch 0): blocks a few draws ahead in a shared-memory ring for path tracing, on demand
+	// in registers for Whitted (most of its rays draw nothing)
+	__shared__ uint32_t rngRingSmem[GI ? FRAY_RNG_RING_WORDS * 128 : 1];
+	typename RenderRng<GI>::type rng;
+	RenderRng<GI>::attach(rng, rngRingSmem, p.roundKeys);
 	PathState<R> ps;
 	Ray<R> rightEye;       // stereo: the second ray is generated up front (src/main.cpp:307-308) and traced afterwards
 	int eye = 0;
@@ -177,6 +192,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 		if (!active && hasItem && cur < end) { // start sample `cur`
 			const int s = cur++;
 			rng.init(p.seed, (uint32_t) (py * p.width + px), (uint32_t) s, 0);
+			rng.ensure((F & FRAY_F_LENS) ? 10 : 2); // pixel offset, two thin-lens samples per eye
 			float ox, oy;
 			sampleOffset(randomOffsets, s, rng, ox, oy);
 			const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 		// ---- one path segment / one ray of the Whitted tree ---------------------------------------------------------------
 		if (active) {
 			bool finished;
-			if (GI) {
+			if constexpr (GI) {
 				finished = !pathSegment<R, F>(sc, ft, ps, rng, eyeCol, cnt);
 			} else {
 				whittedPop<R, F>(sc, ft, rng, ws, eyeCol, cnt);

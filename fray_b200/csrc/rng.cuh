@@ -132,6 +132,7 @@ template <int MODE> struct RngT {
 		init(parent.seed, parent.pixel, parent.sample, branch_);
 		keys = parent.keys;
 	}
+	FRAY_HD void ensure(uint32_t) {} // blocks are generated on demand
 	FRAY_HD void refill()
 	{
 		if (MODE == FRAY_RNG_OUTLINE) blk = philoxBlock(count >> 2, pixel, sample, branch, seed);
@@ -172,6 +173,69 @@ template <int MODE> struct RngT {
 		return a + (int) mulhi32(next(), n);
 	}
 };
+
+#if defined(__CUDACC__)
+// The same streams for the path-tracing kernels, generated a few blocks ahead into a per-thread ring of 16 words in shared
+// memory (layout [word][thread]: conflict-free whatever position each lane is at). A path segment consumes up to 12 draws
+// (src/main.cpp:118-169, 219-236), always at data-dependent positions of the stream; with the blocks in registers every
+// draw paid for a refill test and a four-way select (a tenth of the kernel's instructions). Here ensure(n) runs the ten
+// rounds in ONE loop per call site (three trips for a Lambert segment) and a draw is an address computation and an LDS.
+// Word p of the stream lives in ring[p & 15]; generating block g overwrites block g - 4, so ensure(n) requires n <= 12.
+#define FRAY_RNG_RING_WORDS 16
+struct RngRing {
+	uint32_t pixel, sample, branch;
+	uint32_t count;   // draws consumed
+	uint32_t gen;     // blocks generated
+	uint32_t base;    // shared-memory address of this thread's word 0
+	const uint32_t* keys;
+
+	__device__ __forceinline__ void attach(uint32_t sharedAddr, const uint32_t* keys_) { base = sharedAddr; keys = keys_; }
+	__device__ __forceinline__ void init(uint32_t, uint32_t pixel_, uint32_t sample_, uint32_t branch_)
+	{
+		pixel = pixel_; sample = sample_; branch = branch_; count = 0; gen = 0;
+	}
+	// make the next n draws available (n <= 12)
+	__device__ __forceinline__ void ensure(uint32_t n)
+	{
+		const uint32_t need = (count + n + 3u) >> 2;
+		while (gen < need) {
+			const Philox4 b = philox4x32_10_keyed(gen, pixel, sample, branch, keys);
+			const uint32_t a = base + ((gen & 3u) << 2) * (blockDimRing() * 4u);
+			asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(b.x));
+			asm volatile("st.shared.u32 [%0], %1;" :: "r"(a + blockDimRing() * 4u), "r"(b.y));
+			asm volatile("st.shared.u32 [%0], %1;" :: "r"(a + blockDimRing() * 8u), "r"(b.z));
+			asm volatile("st.shared.u32 [%0], %1;" :: "r"(a + blockDimRing() * 12u), "r"(b.w));
+			gen++;
+		}
+	}
+	static __device__ __forceinline__ uint32_t blockDimRing() { return 128u; } // threads per CTA of the render kernels
+	__device__ __forceinline__ uint32_t next()
+	{
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (count & 15u) * (blockDimRing() * 4u)));
+		count++;
+		return v;
+	}
+	__device__ __forceinline__ void skip(uint32_t n) { count += n; }
+	__device__ __forceinline__ float randfloat() { return (float) (next() >> 8) * (1.0f / 16777216.0f); }
+	__device__ __forceinline__ double randdouble()
+	{
+		const uint64_t lo = next();
+		const uint64_t hi = next();
+		return (double) (((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+	}
+	__device__ __forceinline__ float randdoubleAsFloat()
+	{
+		count++;
+		return (float) (next() >> 8) * (1.0f / 16777216.0f);
+	}
+	__device__ __forceinline__ int randint(int a, int b)
+	{
+		const uint32_t n = (uint32_t) (b - a + 1);
+		return a + (int) mulhi32(next(), n);
+	}
+};
+#endif
 
 typedef RngT<FRAY_RNG_INLINE> Rng;
 

@@ -286,7 +286,7 @@ template <typename R> struct SceneImage {
 					if (dt(cands[c].Nu, N) > 1 - 1e-12) ok = false; // a cap in (or parallel behind) a face plane: leave the mesh alone
 				caps.emplace_back(N, dcap);
 			}
-			if (!ok || members.size() + caps.size() > FRAY_HEX_PLANES || members.size() + caps.size() < 4) continue;
+			if (!ok || members.size() + caps.size() > FRAY_HEX_PLANES || members.size() + caps.size() < 4 || caps.size() > FRAY_HEX_MAX_CAPS) continue;
 			Hex hx;
 			hx.faces = members;
 			hx.caps = caps;
@@ -522,7 +522,7 @@ template <typename R> struct SceneImage {
 		offsets.numFlatSpheres = (int) spheres.size();
 		flatPolys.insert(flatPolys.end(), spheres.begin(), spheres.end());
 		flatInfo.insert(flatInfo.end(), sphereInfo.begin(), sphereInfo.end());
-		// convex hexahedra: header + six planes each (real faces first, then caps, unused slots repeat plane 0)
+		// convex hexahedra: header + six planes each (real faces first, then repeats of plane 0, caps in the last slots)
 		offsets.numFlatHex = (int) hexes.size();
 		for (int l = 0; l < FRAY_SHADOW_LIGHTS; l++) offsets.shadowHex[l] = 0xffffffffu;
 		for (size_t k = 0; k < hexes.size(); k++) {
@@ -530,7 +530,8 @@ template <typename R> struct SceneImage {
 			int4 hd;
 			hd.x = (int) flatInfo.size();
 			hd.y = (int) hx.faces.size();
-			hd.z = hd.w = 0;
+			hd.z = hx.caps.size() == 2 ? 3 : (hx.caps.size() == 1 ? 2 : 0); // which of slots 4, 5 hold caps
+			hd.w = 0;
 			float4 raw;
 			memcpy(&raw, &hd, sizeof(raw));
 			flatPolys.push_back(raw);
@@ -539,8 +540,8 @@ template <typename R> struct SceneImage {
 				planes.push_back(cands[c].rec[0]);
 				flatInfo.push_back(cands[c].fi);
 			}
+			while (planes.size() + hx.caps.size() < FRAY_HEX_PLANES) planes.push_back(planes[0]);
 			for (const auto& cp: hx.caps) planes.push_back(plane4(cp.first, cp.second));
-			while ((int) planes.size() < FRAY_HEX_PLANES) planes.push_back(planes[0]);
 			flatPolys.insert(flatPolys.end(), planes.begin(), planes.end());
 			for (int li = 0; li < s.num_lights && li < FRAY_SHADOW_LIGHTS; li++) {
 				bool can = false;
