@@ -201,6 +201,19 @@ template <typename R> struct DLight {
 	float areaF; // (float) area, as used by RectLight::getNthSample
 };
 
+#define FRAY_LIGHT_REC_VEC 6
+
+FRAY_HD int floatBits(float f) // the int stored in a float4 lane
+{
+#if defined(__CUDA_ARCH__)
+	return __float_as_int(f);
+#else
+	int i;
+	memcpy(&i, &f, sizeof(i));
+	return i;
+#endif
+}
+
 template <typename R> struct DCamera {
 	R pos[3], topLeft[3], topRight[3], bottomLeft[3], front[3], up[3], right[3];
 	R w, h, aperture, focalDist, stereoSep;
@@ -241,6 +254,9 @@ template <typename R> struct DScene {
 	// fast precision only: one 48-byte record per triangle for the KD leaves (intersectMeshFast): plane (N, N.A) with
 	// N = AB ^ AC normalised, and the two barycentric planes lambda2(p) = e2.(p,1), lambda3(p) = e3.(p,1)
 	const float4* kdTris;
+	// fast precision only: FRAY_LIGHT_REC_VEC float4 per light, what explicitLightSample needs in six 128-bit loads:
+	// {type, xSubd, ySubd, samples} {centre, area} {sample-grid corner, 1 / xSubd} {column step} {row step} {colour * power}
+	const float4* lightRecs;
 	// fast precision only (flat.cuh): world-space convex polygons of the brute-force meshes and the rectangular lights
 	const float4* flatPolys;   // FRAY_FLAT_POLY_VEC float4 per polygon
 	const FlatInfo* flatInfo;  // one per polygon
@@ -1453,7 +1469,49 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 	if (lambert) rng.skip(4);
 
 	// explicitLightSample(), src/main.cpp:118-169
-	if (sc.numLights > 0) {
+	if constexpr (!Num<R>::kExact) {
+		// fast precision: the same steps on the compact light records (scene_image.h) -- identical draws, the sample point as
+		// corner + (column + r1) * columnStep + (row + r2) * rowStep instead of through the light's transform
+		if (sc.numLights > 0) {
+			const int li = rng.randint(0, sc.numLights - 1);
+			const float4* rec = sc.lightRecs + FRAY_LIGHT_REC_VEC * li;
+			const float4 hdRaw = rec[0];
+			const int lType = floatBits(hdRaw.x), xSubd = floatBits(hdRaw.y), nSamples = floatBits(hdRaw.w);
+			if (lType == FRAY_LIGHT_RECT) {
+				const float4 ca = rec[1];
+				const float solidAngle = ca.w / fmaxf(1.0f, lengthSqr(h.ip - V3<R>(ca.x, ca.y, ca.z)));
+				if (solidAngle != 0) {
+					const int si = rng.randint(0, nSamples - 1);
+					const float4 c0 = rec[2], cu = rec[3], cv = rec[4];
+					const int row = (int) (((float) si + 0.5f) * c0.w); // exact for the small integers involved, no integer division
+					const int column = si - row * xSubd;
+					const float a = (float) column + rng.randfloat();
+					const float b = (float) row + rng.randfloat();
+					const V3<R> onLight(fmaf(b, cv.x, fmaf(a, cu.x, c0.x)), fmaf(b, cv.y, fmaf(a, cu.y, c0.y)), fmaf(b, cv.z, fmaf(a, cu.z, c0.z)));
+					Col brdf;
+					bool brdfZero;
+					if (lambert) {
+						const V3<R> wOut = normalized(onLight - h.ip);
+						const float cosTerm = fmaxf(0.0f, dot(h.norm, wOut));
+						brdf = loadCol(s.color) * Num<R>::overPi(cosTerm);
+						brdfZero = brdf.intensity() == 0;
+					} else if (s.type == FRAY_SHADER_REFL || s.type == FRAY_SHADER_REFR) {
+						brdfZero = true;
+					} else {
+						brdf = Col(1, 0, 0);
+						brdfZero = false;
+					}
+					// a zero BRDF makes the shadow ray pointless (the reference tests visibility first; same result)
+					if (!brdfZero && visible<R, F>(sc, ft, h.ip + h.norm * eps, onLight, li, cnt)) {
+						const float4 em = rec[5];
+						const float probHit = 1.0f / solidAngle;
+						const float probPick = 1.0f / (float) sc.numLights;
+						accum = accum + Col(em.x, em.y, em.z) * ps.mult * brdf / (probHit * probPick);
+					}
+				}
+			}
+		}
+	} else if (sc.numLights > 0) {
 		const int li = rng.randint(0, sc.numLights - 1);
 		const DLight<R>& L = sc.lights[li];
 		if (L.type == FRAY_LIGHT_RECT) { // solidAngle() == 0 for point lights

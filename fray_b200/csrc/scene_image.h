@@ -749,6 +749,28 @@ template <typename R> struct SceneImage {
 			o.areaF = (float) l.area;
 			if (l.type == FRAY_LIGHT_RECT && (l.x_subd < 1 || l.y_subd < 1)) { err = "RectLight subdivisions must be >= 1"; return false; }
 		}
+		// compact sampling records of the lights for the fast path tracer (core.cuh, LightRec)
+		std::vector<float4> lightRecs((size_t) FRAY_LIGHT_REC_VEC * s.num_lights);
+		for (int i = 0; i < s.num_lights; i++) {
+			const FrayGpuLight& l = s.lights[i];
+			float4* r = lightRecs.data() + (size_t) FRAY_LIGHT_REC_VEC * i;
+			const int nx = std::max(1, l.x_subd), ny = std::max(1, l.y_subd);
+			const int4 hd{ l.type, nx, ny, l.type == FRAY_LIGHT_RECT ? nx * ny : 1 };
+			memcpy(&r[0], &hd, sizeof(float4));
+			r[1] = float4{ (float) l.center[0], (float) l.center[1], (float) l.center[2], (float) l.area };
+			// sample (column + r1, row + r2) of the unit square: T(((column + r1) / nx - 0.5, 0, (row + r2) / ny - 0.5)), src/lights.cpp:49-77
+			const D3 corner = rowMul(D3{ -0.5, 0, -0.5 }, l.T.m);
+			const D3 U = rowMul(D3{ 1.0 / nx, 0, 0 }, l.T.m), V = rowMul(D3{ 0, 0, 1.0 / ny }, l.T.m);
+			if (l.type == FRAY_LIGHT_RECT) {
+				r[2] = float4{ (float) (corner.x + l.T.offset[0]), (float) (corner.y + l.T.offset[1]), (float) (corner.z + l.T.offset[2]), 1.0f / (float) nx };
+				r[3] = float4{ (float) U.x, (float) U.y, (float) U.z, 0.0f };
+				r[4] = float4{ (float) V.x, (float) V.y, (float) V.z, 0.0f };
+			} else {
+				r[2] = float4{ (float) l.pos[0], (float) l.pos[1], (float) l.pos[2], 1.0f };
+				r[3] = r[4] = float4{ 0, 0, 0, 0 };
+			}
+			r[5] = float4{ l.color[0] * l.power, l.color[1] * l.power, l.color[2] * l.power, 0.0f };
+		}
 		std::vector<DNode<R>> nodes(s.num_nodes);
 		for (int i = 0; i < s.num_nodes; i++) {
 			const FrayGpuNode& n = s.nodes[i];
@@ -829,6 +851,7 @@ template <typename R> struct SceneImage {
 		FRAY_PUT(leafRefs, leafRefs);
 		FRAY_PUT(texels, texels);
 		FRAY_PUT(kdTris, kdTris);
+		FRAY_PUT(lightRecs, lightRecs);
 		FRAY_PUT(flatPolys, flatPolys);
 		FRAY_PUT(flatInfo, flatInfo);
 #undef FRAY_PUT
@@ -846,7 +869,7 @@ template <typename R> struct SceneImage {
 		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
 		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
 		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
-		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris);
+		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(lightRecs);
 #undef FRAY_REBASE
 		return d;
 	}
