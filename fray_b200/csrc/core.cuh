@@ -287,10 +287,17 @@ template <typename R> struct Hit {
 	int tri;  // absolute triangle index or -1
 	int mesh; // mesh index (for attribute fetch) or -1
 	int geom; // geometry that produced the hit (CSG side bookkeeping)
+	int flat; // fast precision: FlatInfo index of a hit in the flat table
 };
 
+// per-thread counts: 32 bits in the kernels (a persistent lane traces a few thousand rays per call; the warp sums are 64-bit)
+#if defined(__CUDA_ARCH__)
+typedef unsigned int RayCount;
+#else
+typedef unsigned long long RayCount;
+#endif
 struct RayCounters {
-	unsigned long long rays, primary, shadow;
+	RayCount rays, primary, shadow;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -958,6 +965,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 				light = fi.node;
 			} else {
 				node = fi.node;
+				best.flat = idx;
 				best.ip = ray.start + ray.dir * best.dist;
 				best.norm = V3<R>(fi.nx, fi.ny, fi.nz);
 				best.u = best.v = 0;
@@ -1450,7 +1458,14 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 	       (double) ray.start.z, (double) ray.dir.x, (double) ray.dir.y, (double) ray.dir.z, node, light, (double) h.dist, (double) h.ip.x, (double) h.ip.y, (double) h.ip.z, ps.mult.intensity(), rng.count);
 #endif
 	if (light >= 0) {
-		if (!(ps.flags & FRAY_RF_DIFFUSE)) accum = accum + lightEmission(sc.lights[light]) * ps.mult;
+		if (!(ps.flags & FRAY_RF_DIFFUSE)) {
+			if constexpr (!Num<R>::kExact) {
+				const float4 em = sc.lightRecs[FRAY_LIGHT_REC_VEC * light + 5];
+				accum = accum + Col(em.x, em.y, em.z) * ps.mult;
+			} else {
+				accum = accum + lightEmission(sc.lights[light]) * ps.mult;
+			}
+		}
 		return false;
 	}
 	if (node < 0) {
@@ -1461,7 +1476,21 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 	const DShader<R>& s = sc.shaders[nd.shader];
 	if (F & FRAY_F_TEX) applyBump(sc, nd, h);
 	const R eps = Num<R>::offsetEps(maxAbs(h.ip));
-	const bool lambert = s.type == FRAY_SHADER_LAMBERT;
+	// shader type and colour (Lambert: colour, Refl / Refr: multiplier): from the staged FlatInfo when every hit of this kernel
+	// variant comes out of the flat table, else from the shader table
+	constexpr bool kFlatShade = !Num<R>::kExact && (F & FRAY_F_FLAT) != 0 && (F & (FRAY_F_NODES | FRAY_F_TEX)) == 0;
+	int sType;
+	if constexpr (kFlatShade) sType = floatBits(ft.info[h.flat].shade.x);
+	else sType = s.type;
+	auto shaderCol = [&]() {
+		if constexpr (kFlatShade) {
+			const float4 sh = ft.info[h.flat].shade;
+			return Col(sh.y, sh.z, sh.w);
+		} else {
+			return loadCol((sType == FRAY_SHADER_REFL || sType == FRAY_SHADER_REFR) ? s.mult : s.color);
+		}
+	};
+	const bool lambert = sType == FRAY_SHADER_LAMBERT;
 
 	// all draws of the segment: 4 skipped + 4 for the light sample + 4 for the new direction (Lambert), 4 otherwise
 	rng.ensure(lambert ? 12 : 4);
@@ -1493,9 +1522,9 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 					if (lambert) {
 						const V3<R> wOut = normalized(onLight - h.ip);
 						const float cosTerm = fmaxf(0.0f, dot(h.norm, wOut));
-						brdf = loadCol(s.color) * Num<R>::overPi(cosTerm);
+						brdf = shaderCol() * Num<R>::overPi(cosTerm);
 						brdfZero = brdf.intensity() == 0;
-					} else if (s.type == FRAY_SHADER_REFL || s.type == FRAY_SHADER_REFR) {
+					} else if (sType == FRAY_SHADER_REFL || sType == FRAY_SHADER_REFR) {
 						brdfZero = true;
 					} else {
 						brdf = Col(1, 0, 0);
@@ -1527,9 +1556,9 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 				const V3<R> wOut = normalized(onLight - h.ip);
 				if (lambert) {
 					const float cosTerm = (float) fmax((R) 0, dot(h.norm, wOut));
-					brdf = loadCol(s.color) * Num<R>::overPi(cosTerm);
+					brdf = shaderCol() * Num<R>::overPi(cosTerm);
 					brdfZero = brdf.intensity() == 0;
-				} else if (s.type == FRAY_SHADER_REFL || s.type == FRAY_SHADER_REFR) {
+				} else if (sType == FRAY_SHADER_REFL || sType == FRAY_SHADER_REFR) {
 					brdfZero = true;
 				} else {
 					brdf = Col(1, 0, 0);
@@ -1555,16 +1584,16 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 		ps.dir = hemisphereSample(rng, h.norm);
 		ps.flags |= FRAY_RF_DIFFUSE;
 		const float cosTerm = (float) fmax((R) 0, dot(h.norm, ps.dir));
-		brdf = loadCol(s.color) * Num<R>::overPi(cosTerm);
+		brdf = shaderCol() * Num<R>::overPi(cosTerm);
 		pdf = 0.15915494309189535f; // (float) (1 / (2 * PI))
-	} else if (s.type == FRAY_SHADER_REFL) {
+	} else if (sType == FRAY_SHADER_REFL) {
 		const V3<R> n = faceforward(ray.dir, h.norm);
 		ps.start = h.ip + n * eps;
 		ps.dir = reflect(ray.dir, h.norm);
 		ps.flags &= ~FRAY_RF_DIFFUSE;
-		brdf = loadCol(s.mult) * 1e9f;
+		brdf = shaderCol() * 1e9f;
 		pdf = 1e9f;
-	} else if (s.type == FRAY_SHADER_REFR) {
+	} else if (sType == FRAY_SHADER_REFR) {
 		const V3<R> n = faceforward(ray.dir, h.norm);
 		const R ior = dot(n, h.norm) > 0 ? 1 / s.ior : s.ior;
 		V3<R> refracted;
@@ -1572,7 +1601,7 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 			ps.start = h.ip - n * eps;
 			ps.dir = refracted;
 			ps.flags &= ~FRAY_RF_DIFFUSE;
-			brdf = loadCol(s.mult) * 1e9f;
+			brdf = shaderCol() * 1e9f;
 			pdf = 1e9f;
 		} else {
 			brdf = Col(0, 0, 0); // total internal reflection: the path goes on with zero throughput and is cut next round

@@ -250,15 +250,16 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 :
 	}
 
 	// statistics: one atomic per warp
+	unsigned long long nRays = cnt.rays, nPrimary = cnt.primary, nShadow = cnt.shadow;
 	for (int m = 16; m > 0; m >>= 1) {
-		cnt.rays += __shfl_xor_sync(0xffffffffu, cnt.rays, m);
-		cnt.primary += __shfl_xor_sync(0xffffffffu, cnt.primary, m);
-		cnt.shadow += __shfl_xor_sync(0xffffffffu, cnt.shadow, m);
+		nRays += __shfl_xor_sync(0xffffffffu, nRays, m);
+		nPrimary += __shfl_xor_sync(0xffffffffu, nPrimary, m);
+		nShadow += __shfl_xor_sync(0xffffffffu, nShadow, m);
 	}
 	if (lane == 0) {
-		atomicAdd(p.counters + 0, cnt.rays);
-		atomicAdd(p.counters + 1, cnt.primary);
-		atomicAdd(p.counters + 2, cnt.shadow);
+		atomicAdd(p.counters + 0, nRays);
+		atomicAdd(p.counters + 1, nPrimary);
+		atomicAdd(p.counters + 2, nShadow);
 		if (ws.overflow) atomicExch(p.errorFlag, 1);
 	}
 }

@@ -552,6 +552,14 @@ template <typename R> struct SceneImage {
 			feat |= FRAY_F_HEX;
 		}
 		offsets.numFlatInfo = (int) flatInfo.size();
+		for (FlatInfo& fi: flatInfo) {
+			if (fi.flags & FRAY_FLAT_LIGHT) continue;
+			const FrayGpuShader& sh = s.shaders[s.nodes[fi.node].shader];
+			const float* c = (sh.type == FRAY_SHADER_REFL || sh.type == FRAY_SHADER_REFR) ? sh.mult : sh.color;
+			const int4 t{ sh.type, 0, 0, 0 };
+			memcpy(&fi.shade, &t, sizeof(float4));
+			fi.shade.y = c[0]; fi.shade.z = c[1]; fi.shade.w = c[2];
+		}
 		if (getenv("FRAY_GPU_VERBOSE")) {
 			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records, %d spheres, %d convex hexahedra", offsets.numFlatGeom,
 			        offsets.numFlatAll - offsets.numFlatGeom, offsets.numFlatSpheres, offsets.numFlatHex);

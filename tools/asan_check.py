@@ -43,11 +43,11 @@ def main():
         assert lib.fray_emul_render(scene.flat, C.byref(frame), out.ctypes.data, C.byref(stats), precision, 4) == 0
         assert kw.get("mode", fb.RENDER_BEAUTY) != fb.RENDER_BEAUTY or np.isfinite(out).all()  # a miss has distance inf in the AOV
 
-    scenes = [golden_scene(cases, name) for name in cases]
+    todo = [golden_scene(cases, name) for name in cases]
     extra = os.path.join(scenes.DATA_DIR, "flat_transforms__test.fray")
     shutil.copyfile(os.path.join(ROOT, "tests", "scenes", "flat_transforms.fray"), extra)
-    scenes.append((extra, 7))
-    for path, seed in scenes:
+    todo.append((extra, 7))
+    for path, seed in todo:
         sc = fb.Scene(path)
         for precision in (fb.FP32, fb.FP64):
             render(sc, precision, seed=seed)
