@@ -55,6 +55,7 @@ struct FlatInfo {
 	float4 diag;        // FRAY_FLAT_QUAD: diag . (p, 1) < 0 <=> p lies in tri1
 	float4 shade;       // the node's shader as the path tracer needs it: {type (int bits), r, g, b} with the colour of a Lambert
 	                    // shader or the multiplier of a reflection / refraction (textured variants read the shader table instead)
+	float4 pad;         // 80-byte stride: lanes that fetch different entries from shared memory spread over eight bank groups
 };
 
 // t = h / s. On the GPU: one MUFU.RCP and one FMUL (the records are scaled at upload so that neither over- nor underflows)

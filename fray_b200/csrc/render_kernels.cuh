@@ -111,7 +111,7 @@ template <> struct RenderRng<true> {
 };
 
 template <typename R, bool GI, int F>
-__global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 6 : (Num<R>::kExact ? 1 : (GI ? 6 : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
+__global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 : (Num<R>::kExact ? 1 : (GI ? 6 : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u;
