@@ -73,9 +73,10 @@ __global__ void combineKernel(const RenderParams p)
 	for (unsigned slot = blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += gridDim.x * blockDim.x) {
 		int px, py;
 		if (!slotPixel(p, slot, px, py)) continue;
-		const float* c = p.scratch + 3 * (size_t) slot * p.numChunks;
+		const float* c = p.scratch + 3 * (size_t) slot; // chunk-major: consecutive threads read consecutive triples
+		const size_t stride = 3 * (size_t) slots;
 		Col sum(0, 0, 0);
-		for (int k = 0; k < p.numChunks; k++) sum = sum + Col(c[3 * k], c[3 * k + 1], c[3 * k + 2]);
+		for (int k = 0; k < p.numChunks; k++, c += stride) sum = sum + Col(c[0], c[1], c[2]);
 		if (!p.sumOnly) sum = sum / (float) p.spp;
 		float* o = p.out + 3 * ((size_t) py * p.width + px);
 		o[0] = sum.r; o[1] = sum.g; o[2] = sum.b;
@@ -278,12 +279,13 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	p.width = c->width; p.height = c->height; p.spp = spp; p.s0 = s0; p.s1 = s1; p.seed = f->seed;
 	philoxRoundKeys(p.seed, p.roundKeys);
 	p.sumOnly = (f->flags & FRAY_FRAME_SUM) ? 1 : 0;
-	// chunk size: every lane of the grid should see >= ~20 items (measured optimum for a 1.5 ms call: 2 paths per item), so that the drain at the end of the kernel (lanes running
-	// dry while the last items finish; an item of C paths takes C x ~35 us on a busy SM) is a few percent of the call even
-	// when 8 GPUs share a frame; the scratch buffer (one RGB sum per pixel and chunk) is kept below 192 MB
+	// chunk size: every lane of the grid should see >= ~16 items, so that the drain at the end of the kernel (lanes running dry
+	// while the last items finish; an item of C paths takes C x ~35 us on a busy SM) is a few percent of the call even when 8 GPUs
+	// share a frame. Measured on a 1/8 share of the headline frame (tools/share_time.py, 1.10 ms of work): C = 1 1.229 ms,
+	// C = 2 1.204 ms, C = 4 1.233 ms, C = 8 1.289 ms. The scratch buffer (one RGB sum per pixel and chunk) is kept below 192 MB
 	const int samples = std::max(1, s1 - s0);
 	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) cfg.gridBlocks * 128.0);
-	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 20.0)));
+	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 16.0)));
 	const double maxChunks = std::max(1.0, 192e6 / ((double) ownedTiles * 32.0 * 12.0));
 	C = std::max(C, (int) ((samples + maxChunks - 1) / maxChunks));
 	if (const char* e = getenv("FRAY_GPU_CHUNK")) C = std::max(1, atoi(e)); // experiments only

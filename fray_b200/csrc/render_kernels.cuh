@@ -42,7 +42,7 @@ struct RenderParams {
 	int taskStride, taskOffset; // owned tile j is tile j * taskStride + taskOffset of the frame
 	unsigned int totalItems;    // numOwnedTiles * 32 * numChunks
 	float* out;       // [height][width][3]
-	float* scratch;   // numChunks > 1: [owned pixel slot][chunk][3]
+	float* scratch;   // numChunks > 1: [chunk][owned pixel slot][3]
 	unsigned long long* counters; // rays, primary, shadow
 	unsigned int* workCounter;
 	int* errorFlag;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 :
 					cur = p.s0 + (int) chunk * p.chunk;
 					end = min(cur + p.chunk, p.s1);
 					accum = Col(0, 0, 0);
-					outIndex = p.numChunks == 1 ? (unsigned) (py * p.width + px) : slot * (unsigned) p.numChunks + chunk;
+					outIndex = p.numChunks == 1 ? (unsigned) (py * p.width + px) : chunk * ((unsigned) p.numOwnedTiles * 32u) + slot;
 				}
 				want = false; // a slot outside the image is simply dropped; the lane asks again next round
 			}
