@@ -285,7 +285,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	// C = 2 1.204 ms, C = 4 1.233 ms, C = 8 1.289 ms. The scratch buffer (one RGB sum per pixel and chunk) is kept below 192 MB
 	const int samples = std::max(1, s1 - s0);
 	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) cfg.gridBlocks * 128.0);
-	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 16.0)));
+	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 32.0)));
 	const double maxChunks = std::max(1.0, 192e6 / ((double) ownedTiles * 32.0 * 12.0));
 	C = std::max(C, (int) ((samples + maxChunks - 1) / maxChunks));
 	if (const char* e = getenv("FRAY_GPU_CHUNK")) C = std::max(1, atoi(e)); // experiments only

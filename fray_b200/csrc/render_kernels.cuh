@@ -114,8 +114,10 @@ template <typename R, bool GI, int F>
 __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 : (Num<R>::kExact ? 1 : (GI ? 6 : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
-	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const unsigned ltMask = (1u << lane) - 1u;
+	__shared__ uint2 stagedItem[4][32]; // per warp, the decoded items of its pool batch: {px | py << 16 (all ones: outside the image), output index}
+	__shared__ int stagedCur[4];        // first sample of the batch's chunk
 	const bool randomOffsets = sc.cam.dof || sc.gi;
 	const bool stereo = (F & FRAY_F_LENS) && sc.cam.stereoSep > 0;
 
@@ -166,23 +168,33 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 :
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if (base >= p.totalItems) { exhausted = true; break; }
 				poolNext = base;
-				poolEnd = min(base + (unsigned) FRAY_POOL_BATCH, p.totalItems);
+				poolEnd = base + (unsigned) FRAY_POOL_BATCH; // totalItems is a multiple of the batch
+				// The batch is one (owned tile, chunk) pair: id = (ownedTile * numChunks + chunk) * 32 + within. Every lane decodes
+				// item base + lane, once per 32 items and with all lanes busy, and parks it in shared memory for whoever takes it.
+				unsigned chunk, j;
+				divmodSmall(base >> 5, (unsigned) p.numChunks, p.invNumChunks, p.exactDiv != 0, j, chunk);
+				const unsigned slot = (j << 5) | lane;
+				int qx, qy;
+				uint2 st;
+				st.x = slotPixel(p, slot, qx, qy) ? ((unsigned) qx | ((unsigned) qy << 16)) : 0xffffffffu;
+				st.y = p.numChunks == 1 ? (unsigned) (qy * p.width + qx) : chunk * ((unsigned) p.numOwnedTiles * 32u) + slot;
+				__syncwarp();
+				stagedItem[warp][lane] = st;
+				if (lane == 0) stagedCur[warp] = p.s0 + (int) chunk * p.chunk;
+				__syncwarp();
 			}
 			const unsigned avail = poolEnd - poolNext;
 			const unsigned rank = __popc(wanters & ltMask);
 			if (want && rank < avail) {
-				const unsigned id = poolNext + rank;
-				// id = (ownedTile * numChunks + chunk) * 32 + within
-				const unsigned within = id & 31u, tc = id >> 5;
-				unsigned chunk, j;
-				divmodSmall(tc, (unsigned) p.numChunks, p.invNumChunks, p.exactDiv != 0, j, chunk);
-				const unsigned slot = (j << 5) | within;
-				if (slotPixel(p, slot, px, py)) {
+				const uint2 st = stagedItem[warp][(poolNext + rank) & 31u];
+				if (st.x != 0xffffffffu) {
 					hasItem = true;
-					cur = p.s0 + (int) chunk * p.chunk;
+					px = (int) (st.x & 0xffffu);
+					py = (int) (st.x >> 16);
+					cur = stagedCur[warp];
 					end = min(cur + p.chunk, p.s1);
 					accum = Col(0, 0, 0);
-					outIndex = p.numChunks == 1 ? (unsigned) (py * p.width + px) : chunk * ((unsigned) p.numOwnedTiles * 32u) + slot;
+					outIndex = st.y;
 				}
 				want = false; // a slot outside the image is simply dropped; the lane asks again next round
 			}

@@ -577,6 +577,7 @@ template <typename R> struct SceneImage {
 		features = 0;
 		if (s.abi_version != FRAY_GPU_ABI_VERSION) { err = "FrayGpuScene.abi_version mismatch"; return false; }
 		if (s.num_nodes < 0 || s.num_lights < 0 || s.settings.frame_width <= 0 || s.settings.frame_height <= 0) { err = "malformed scene header"; return false; }
+		if (s.settings.frame_width > 65535 || s.settings.frame_height > 65535) { err = "frame larger than 65535 pixels a side"; return false; } // pixel coordinates travel as 16-bit pairs
 		auto inRange = [](long long i, long long n) { return i >= 0 && i < n; };
 
 		DScene<R>& d = offsets;
