@@ -34,7 +34,7 @@ UNIT = "Mrays/s"
 # 6.45 triangle tests, 0.54 light tests, 0.46 light samples, 0.86 hemisphere samples, 0.36 BRDF evals per ray
 FLOP_PER_RAY = 937.0
 BYTES_PER_RAY = 1430.0
-NCU_DRAM_BYTES_PER_LAUNCH = 44544 + 121856
+NCU_DRAM_BYTES_PER_LAUNCH = 135424 + 14864896
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x FP32 lanes x 2 (FMA) x max SM clock
 
 
@@ -136,11 +136,12 @@ def run_reference(args, rank: int, world: int):
 
 
 def cpu_baseline(log_fn) -> dict:
-    """The reference's own CPU renderer on a bounded sample (rank 0, N=1 only): ~10-30 s of CPU work."""
+    """The reference's own CPU renderer on the same frame (rank 0, N=1 only): ~25 s of CPU work (one pass of the oracle port for
+    the ray count and the work profile, two of the reference binary)."""
     import fray_b200 as fb
     import oracle_util as ou
     cores = min(64, os.cpu_count() or 1)
-    sample_spp = 40
+    sample_spp = SPP  # the whole 256-path frame: ~8 s per frame on 16 threads, ~25 s for this leg
     f = bench_scene_file(sample_spp, dict(numThreads=cores, wantPrepass="off"))
     sc = fb.Scene(f)
     t = time.time()
@@ -160,7 +161,7 @@ def cpu_baseline(log_fn) -> dict:
     log_fn(f"cpu baseline ({kind}, {cores} threads): {sec:.2f} s for {ostats.rays} rays; oracle port {port_sec:.2f} s; "
            f"algorithmic work {flop:.0f} flop/ray {byts:.0f} B/ray")
     return {"value": ostats.rays / sec / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"cornell_box.fray 400x400 at {sample_spp} paths/pixel ({ostats.rays} rays), best of 2 frames",
+            "sample": f"cornell_box.fray 400x400 at {sample_spp} paths/pixel, the full frame ({ostats.rays} rays by the reference's count), best of 2 frames",
             "ms_per_frame_sample": sec * 1e3, "flop_per_ray_measured": flop, "bytes_per_ray_measured": byts}
 
 
@@ -292,7 +293,8 @@ def main():
         roofline = {
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the ncu --set full
-            # capture profiles/r01_v12_cornell256_ncu_summary.txt (45 KB read + 122 KB written): the scene and the frame stay in L2
+            # capture profiles/r01_v23_cornell256_ncu_summary.txt (0.14 MB read + 14.9 MB written: the part of the 61 MB chunk-sum scratch
+            # that left the L2 during the cold, serialised ncu pass; the scene tables never leave the SMs)
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.spp == SPP and world == 1 and precision == fb.FP32) else None,
             "peak_source": "FFMA micro-benchmark run in this process (fray_gpu_measure_peaks); MEASURED_PEAKS.json holds no FP32 figure",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
