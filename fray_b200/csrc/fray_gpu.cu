@@ -442,6 +442,81 @@ int fray_gpu_resolve_device(FrayGpuCtx* c, const void* d_sum, void* d_rgb, int32
 	return FRAY_GPU_OK;
 }
 
+// ---- random-stream self-test ---------------------------------------------------------------------------
+struct RngProbeParams {
+	uint32_t seed, pixel, sample, branch;
+	uint32_t roundKeys[10];
+	int mode, n;
+	uint32_t* out;
+	unsigned char* drawn;
+};
+
+// 128 threads as in the render kernels (the ring layout depends on it); thread 77 runs the probe, the others run decoy
+// streams through the same ring so that a layout mistake would show
+__global__ void rngProbeKernel(const RngProbeParams p)
+{
+	__shared__ uint32_t ring[FRAY_RNG_RING_WORDS * 128];
+	const bool probe = threadIdx.x == 77;
+	const uint32_t pixel = probe ? p.pixel : p.pixel + 1000u + threadIdx.x;
+	int i = 0;
+	auto put = [&](uint32_t v) { if (probe) { p.out[i] = v; p.drawn[i] = 1; } i++; };
+	if (p.mode == 0) {
+		RngT<FRAY_RNG_KEYED> rng;
+		rng.keys = p.roundKeys;
+		rng.init(p.seed, pixel, p.sample, p.branch);
+		while (i < p.n) put(rng.next());
+		return;
+	}
+	RngRing rng;
+	rng.attach((uint32_t) __cvta_generic_to_shared(ring + threadIdx.x), p.roundKeys);
+	rng.init(p.seed, pixel, p.sample, p.branch);
+	if (p.mode == 1) {
+		while (i < p.n) {
+			const int group = min(12, p.n - i);
+			rng.ensure((uint32_t) group);
+			for (int k = 0; k < group; k++) put(rng.next());
+		}
+		return;
+	}
+	rng.ensure(2);
+	for (int k = 0; k < 2 && i < p.n; k++) put(rng.next());
+	while (i + 12 <= p.n) {
+		rng.ensure(12);
+		rng.skip(4); i += 4;
+		for (int k = 0; k < 4; k++) put(rng.next());
+		for (int k = 0; k < 2; k++) { rng.skip(1); i++; put(rng.next()); }
+	}
+}
+
+int fray_gpu_rng_probe(int device, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t branch, int mode, int n, uint32_t* out, unsigned char* drawn)
+{
+	if (!out || !drawn || n < 0 || mode < 0 || mode > 2) return fail(FRAY_GPU_EINVAL, "bad argument");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(FRAY_GPU_ENODEVICE, "no CUDA device available");
+	}
+	if (device < 0 || device >= ndev) return fail(FRAY_GPU_EINVAL, "device ordinal out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	memset(out, 0, sizeof(uint32_t) * (size_t) n);
+	memset(drawn, 0, (size_t) n);
+	if (n == 0) return FRAY_GPU_OK;
+	RngProbeParams p;
+	p.seed = seed; p.pixel = pixel; p.sample = sample; p.branch = branch; p.mode = mode; p.n = n;
+	philoxRoundKeys(seed, p.roundKeys);
+	CUDA_TRY(cudaMalloc(&p.out, sizeof(uint32_t) * (size_t) n));
+	CUDA_TRY(cudaMalloc(&p.drawn, (size_t) n));
+	CUDA_TRY(cudaMemset(p.out, 0, sizeof(uint32_t) * (size_t) n));
+	CUDA_TRY(cudaMemset(p.drawn, 0, (size_t) n));
+	rngProbeKernel<<<1, 128>>>(p);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpy(out, p.out, sizeof(uint32_t) * (size_t) n, cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemcpy(drawn, p.drawn, (size_t) n, cudaMemcpyDeviceToHost));
+	cudaFree(p.out);
+	cudaFree(p.drawn);
+	return FRAY_GPU_OK;
+}
+
 int fray_gpu_measure_peaks(int device, double ms, double* fp32_tflops, double* l2_gbs)
 {
 	int ndev = 0;

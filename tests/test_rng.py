@@ -2,6 +2,7 @@
 import ctypes as C
 
 import numpy as np
+import pytest
 
 import fray_b200 as fb
 import oracle_util as ou
@@ -47,3 +48,25 @@ def test_streams_differ_by_pixel_and_sample():
         assert not np.array_equal(base, _draws(host.fray_host_rng_draws, *args, 16))
     # draw i is word (i & 3) of block (i >> 2): a longer request starts with the shorter one
     assert np.array_equal(base[:7], _draws(host.fray_host_rng_draws, 42, 10, 3, 0, 7))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_device_streams_equal_the_contract(mode):
+    """The forms the kernels generate their streams in -- on-demand blocks with round keys from the kernel parameters, and the
+    path tracer's shared-memory ring, sequentially and under pathSegment's skip / draw pattern -- against the oracle's RNG."""
+    gpu, oracle = fb.gpu_lib(), ou.oracle_lib()
+    gpu.fray_gpu_rng_probe.argtypes = [C.c_int] + [C.c_uint32] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rs = np.random.RandomState(11 + mode)
+    for _ in range(12):
+        seed, pixel, sample, branch = (int(v) for v in rs.randint(0, 2 ** 32, size=4, dtype=np.uint64))
+        n = int(rs.randint(1, 200))
+        out, drawn = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint8)
+        assert gpu.fray_gpu_rng_probe(0, seed, pixel, sample, branch, mode, n, out.ctypes.data, drawn.ctypes.data) == 0
+        want = _draws(oracle.fray_oracle_rng_draws, seed, pixel, sample, branch, n)
+        got = drawn.astype(bool)
+        if mode < 2:
+            assert got.all()
+        else:  # 2 draws, then 6 of every 12
+            assert got.sum() == min(n, 2) + 6 * ((n - 2) // 12 if n >= 2 else 0)
+        assert np.array_equal(out[got], want[got])
