@@ -1247,9 +1247,16 @@ template <typename R> struct RayTask {
 #define FRAY_TASK_STACK 32
 
 template <typename R> struct WhittedState {
-	RayTask<R> stack[FRAY_TASK_STACK];
+	RayTask<R> stack[FRAY_TASK_STACK]; // local memory on the GPU
 	int sp;
 	int overflow;
+	// the root ray of a sample waits here (registers) instead of making a round trip through the stack: most samples of the
+	// Whitted scenes are a primary ray and its shadow rays, and a stack entry is 21 words of local memory per lane
+	bool rootPending;
+	V3<R> rootStart, rootDir;
+
+	FRAY_HD void setRoot(const V3<R>& start, const V3<R>& dir) { rootStart = start; rootDir = dir; rootPending = true; sp = 0; }
+	FRAY_HD bool done() const { return sp == 0 && !rootPending; }
 };
 
 // Reflection::shade (src/shading.cpp:160-205), Refraction::shade (:238-263), Layered::shade (:357-367), expressed as
@@ -1363,7 +1370,15 @@ FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R
 template <typename R, int F, typename RNG>
 FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, RNG& primary, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
-	const RayTask<R> t = ws.stack[--ws.sp];
+	RayTask<R> t;
+	if (ws.rootPending) {
+		ws.rootPending = false;
+		t.start = ws.rootStart; t.dir = ws.rootDir; t.weight = Col(1, 1, 1);
+		t.depth = 0; t.branch = 0; t.count = 0; t.kind = FRAY_TASK_RAY;
+		t.n = V3<R>(0, 0, 0); t.shader = 0; t.k = 0; t.ns = 0; t.k0 = 0;
+	} else {
+		t = ws.stack[--ws.sp];
+	}
 	if (t.kind == FRAY_TASK_GLOSSY) {
 		// sample t.k of a glossy reflection: Reflection::shade, src/shading.cpp:176-200
 		const DShader<R>& s = sc.shaders[t.shader];
@@ -1699,17 +1714,8 @@ FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, 
 			ps.flags = 0;
 			while (pathSegment<R, F>(sc, ft, ps, rng, c, cnt)) {}
 		} else {
-			RayTask<R> root;
-			root.kind = FRAY_TASK_RAY;
-			root.start = rays[e].start;
-			root.dir = rays[e].dir;
-			root.weight = Col(1, 1, 1);
-			root.depth = 0;
-			root.branch = 0;
-			root.count = 0;
-			ws->stack[0] = root;
-			ws->sp = 1;
-			while (ws->sp > 0) whittedPop<R, F>(sc, ft, rng, *ws, c, cnt);
+			ws->setRoot(rays[e].start, rays[e].dir);
+			while (!ws->done()) whittedPop<R, F>(sc, ft, rng, *ws, c, cnt);
 		}
 		if (stereo) {
 			if (sc.saturation != 1) c = adjustSaturation(c, sc.saturation);

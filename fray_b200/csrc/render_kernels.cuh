@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 :
 	WhittedState<R> ws; // only touched by the Whitted instantiation
 	ws.sp = 0;
 	ws.overflow = 0;
+	ws.rootPending = false;
 
 	// warp-level item pool [poolNext, poolEnd): identical in all lanes
 	unsigned poolNext = 0, poolEnd = 0;
@@ -216,11 +217,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 :
 			if (GI) {
 				ps.start = first.start; ps.dir = first.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
 			} else {
-				RayTask<R> root;
-				root.start = first.start; root.dir = first.dir; root.weight = Col(1, 1, 1);
-				root.depth = 0; root.branch = 0; root.count = 0; root.kind = FRAY_TASK_RAY;
-				ws.stack[0] = root;
-				ws.sp = 1;
+				ws.setRoot(first.start, first.dir);
 			}
 			active = true;
 		}
@@ -233,7 +230,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 :
 				finished = !pathSegment<R, F>(sc, ft, ps, rng, eyeCol, cnt);
 			} else {
 				whittedPop<R, F>(sc, ft, rng, ws, eyeCol, cnt);
-				finished = ws.sp == 0;
+				finished = ws.done();
 			}
 			if (finished) {
 				if (stereo) {
@@ -248,11 +245,7 @@ __global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 :
 					if (GI) {
 						ps.start = rightEye.start; ps.dir = rightEye.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
 					} else {
-						RayTask<R> root;
-						root.start = rightEye.start; root.dir = rightEye.dir; root.weight = Col(1, 1, 1);
-						root.depth = 0; root.branch = 0; root.count = 0; root.kind = FRAY_TASK_RAY;
-						ws.stack[0] = root;
-						ws.sp = 1;
+						ws.setRoot(rightEye.start, rightEye.dir);
 					}
 				} else {
 					active = false;

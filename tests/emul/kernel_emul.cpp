@@ -20,6 +20,8 @@ static void renderRows(const DScene<R>& sc, const FlatTab& ft, const FrayGpuFram
 {
 	WhittedState<R>* ws = new WhittedState<R>;
 	ws->overflow = 0;
+	ws->rootPending = false;
+	ws->sp = 0;
 	RayCounters cnt = { 0, 0, 0 };
 	const int bcount = fr.bucket_count > 0 ? fr.bucket_count : 1, brank = fr.bucket_count > 0 ? fr.bucket_rank : 0;
 	for (;;) {
