@@ -98,6 +98,11 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 	return ft;
 }
 
+// resident CTAs per SM the Whitted kernels with a generic node loop (KD walks: latency-bound) are compiled for
+#ifndef FRAY_WHITTED_KD_CTAS
+#define FRAY_WHITTED_KD_CTAS 6
+#endif
+
 template <bool GI> struct RenderRng {
 	typedef RngT<FRAY_RNG_KEYED> type;
 	static __device__ __forceinline__ void attach(type& rng, uint32_t*, const uint32_t* keys) { rng.keys = keys; }
@@ -111,7 +116,7 @@ template <> struct RenderRng<true> {
 };
 
 template <typename R, bool GI, int F>
-__global__ void __launch_bounds__(128, (F == Variants<float>::kLean && GI) ? 7 : (Num<R>::kExact ? 1 : (GI ? 6 : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
+__global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? ((F == Variants<float>::kLean) ? 7 : 6) : ((F & FRAY_F_NODES) ? FRAY_WHITTED_KD_CTAS : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
