@@ -60,19 +60,6 @@ FRAY_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
 	return Philox4{ c0, c1, c2, c3 };
 }
 
-// One block of a stream. On the GPU this is ONE out-of-line copy per kernel (arguments and result travel in registers):
-// the ten rounds are ~60 instructions, a path segment needs three blocks and a new sample one, and four inlined copies
-// were what pushed the hot loop of the path tracer out of the 32 KB instruction cache.
-#if defined(__CUDACC__)
-static __host__ __device__ __noinline__
-#else
-inline
-#endif
-Philox4 philoxBlock(uint32_t block, uint32_t pixel, uint32_t sample, uint32_t branch, uint32_t seed)
-{
-	return philox4x32_10(block, pixel, sample, branch, seed, 0x46524159u);
-}
-
 FRAY_HD uint32_t rngMix(uint32_t v)
 {
 	v = (v ^ (v >> 16)) * 0x7FEB352Du;
@@ -111,10 +98,9 @@ FRAY_HD void philoxRoundKeys(uint32_t seed, uint32_t* keys)
 	for (int i = 0; i < 10; i++) keys[i] = seed + (uint32_t) i * 0x9E3779B9u;
 }
 
-// How a stream generates its blocks: inline from the seed (host code, the Whitted kernels), through the out-of-line
-// philoxBlock (one copy of the ten rounds per kernel), or inline with a round-key table (the render kernels: `keys` points
-// at RenderParams::roundKeys, i.e. into the kernel's constant bank).
-enum { FRAY_RNG_INLINE = 0, FRAY_RNG_OUTLINE = 1, FRAY_RNG_KEYED = 2 };
+// How a stream generates its blocks: inline from the seed (host code) or inline with a round-key table (the render kernels:
+// `keys` points at RenderParams::roundKeys, i.e. into the kernel's constant bank).
+enum { FRAY_RNG_INLINE = 0, FRAY_RNG_KEYED = 2 };
 
 template <int MODE> struct RngT {
 	uint32_t seed, pixel, sample, branch;
@@ -135,8 +121,7 @@ template <int MODE> struct RngT {
 	FRAY_HD void ensure(uint32_t) {} // blocks are generated on demand
 	FRAY_HD void refill()
 	{
-		if (MODE == FRAY_RNG_OUTLINE) blk = philoxBlock(count >> 2, pixel, sample, branch, seed);
-		else if (MODE == FRAY_RNG_KEYED) blk = philox4x32_10_keyed(count >> 2, pixel, sample, branch, keys);
+		if (MODE == FRAY_RNG_KEYED) blk = philox4x32_10_keyed(count >> 2, pixel, sample, branch, keys);
 		else blk = philox4x32_10(count >> 2, pixel, sample, branch, seed, 0x46524159u);
 	}
 	FRAY_HD uint32_t next()
