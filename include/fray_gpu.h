@@ -194,7 +194,7 @@ typedef struct FrayGpuCamera {
 
 /* struct GlobalSettings, src/scene.h:252-278 (only what the render loop reads) */
 typedef struct FrayGpuSettings {
-	int32_t frame_width, frame_height;
+	int32_t frame_width, frame_height; /* 1 .. 65535 each (the reference stops at VFB_MAX_SIZE = 3000, src/constants.h:27) */
 	int32_t max_trace_depth;
 	int32_t gi;
 	int32_t num_paths;
