@@ -62,6 +62,66 @@ def test_flat_table_on_the_gpu(scene):
     assert ou.compare(want, got, 2e-5)[0] == 1.0 and stats.rays == ostats.rays
 
 
+# ---- convex hexahedra with two cap planes: an open tube ---------------------------------------------------------------
+OPEN_TUBE_OBJ = """# open square tube: four side faces seen from outside, no top, no bottom
+v -1 0 -1
+v  1 0 -1
+v  1 0  1
+v -1 0  1
+v -1 1 -1
+v  1 1 -1
+v  1 1  1
+v -1 1  1
+f 1 5 6 2
+f 2 6 7 3
+f 3 7 8 4
+f 4 8 5 1
+"""
+
+
+@pytest.fixture(scope="module")
+def tube_scene(data_dir):
+    with open(os.path.join(data_dir, "geom", "open_tube__test.obj"), "w") as f:
+        f.write(OPEN_TUBE_OBJ)
+    dst = os.path.join(data_dir, "open_tube__test.fray")
+    shutil.copyfile(os.path.join(HERE, "scenes", "open_tube.fray"), dst)
+    return fb.Scene(dst)
+
+
+def check_tube(scene, render):
+    want, ostats = ou.oracle_render(scene, seed=5)
+    waov, _ = ou.oracle_render(scene, mode=fb.RENDER_AOV)
+    assert {0, 1, 2} <= set(np.unique(waov[..., 0]).astype(int))
+    # the camera does look into the standing tube: floor pixels surrounded by tube pixels
+    got, stats = render(scene, fb.FP32, seed=5)
+    frac, rmse, mx = ou.compare(want, got, 1e-3)
+    assert frac >= 0.995 and rmse < 5e-3, (frac, rmse, mx)
+    assert abs(stats.rays - ostats.rays) <= 0.002 * ostats.rays
+    gaov, _ = render(scene, fb.FP32, mode=fb.RENDER_AOV)
+    assert (gaov[..., 0] == waov[..., 0]).mean() >= 0.998
+
+
+def test_open_tube_on_the_host_emulator(tube_scene, capfd):
+    from test_emul_vs_oracle import emul as emul_fixture
+    render = emul_fixture.__wrapped__()
+    os.environ["FRAY_GPU_VERBOSE"] = "1"
+    try:
+        check_tube(tube_scene, render)
+    finally:
+        del os.environ["FRAY_GPU_VERBOSE"]
+    assert "2 convex hexahedra" in capfd.readouterr().err  # both tubes became six-plane solids (four faces + two caps)
+
+
+@pytest.mark.gpu
+def test_open_tube_on_the_gpu(tube_scene):
+    def render(sc, precision, **kw):
+        ctx = fb.GpuContext(sc, 0, precision)
+        out = ctx.render(**kw)
+        ctx.close()
+        return out
+    check_tube(tube_scene, render)
+
+
 # ---- degenerate inputs: nothing to hit, nothing to light with, frames that are not a multiple of the 8x4 tile ----
 EMPTY = """
 GlobalSettings {
