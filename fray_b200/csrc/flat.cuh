@@ -188,11 +188,12 @@ FRAY_HD bool flatHexTest(const float4* __restrict__ planes, float ox, float oy, 
 		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, fmaf(pl.z, dz, 0.0f)));
 		const float h = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
 		const float t = flatDivide(h, s);
+		// written as guarded updates, not selects: they compile to predicated moves / min instead of compare + select pairs,
+		// which halves the work of the ALU pipe, the busy one in this loop
 		const bool front = s < 0.0f;
 		const bool better = front & (t > tHit); // strict: a repeated plane never replaces the original
-		tHit = better ? t : tHit;
-		jHit = better ? j : jHit;
-		tBound = fminf(tBound, front ? inf : t);
+		if (better) { tHit = t; jHit = j; }
+		if (!front) tBound = fminf(tBound, t);
 	}
 	return (tHit <= tBound) & (tHit >= 0.0f);
 }
@@ -216,7 +217,7 @@ FRAY_HD void flatHexClosest(const float4* __restrict__ H, int n, float ox, float
 FRAY_HD bool flatHexAnyTest(const float4* __restrict__ planes, bool cap4, bool cap5, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
 {
 	const float inf = 3.0e38f;
-	float tIn[FRAY_HEX_PLANES], tOut[FRAY_HEX_PLANES];
+	float tHit = -inf, tLow = -inf, tBound = inf;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -225,13 +226,12 @@ FRAY_HD bool flatHexAnyTest(const float4* __restrict__ planes, bool cap4, bool c
 		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, fmaf(pl.z, dz, 0.0f))); // +0 seed: see flatHexTest
 		const float h = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
 		const float t = flatDivide(h, s);
+		const bool cap = (j == 4 && cap4) || (j == 5 && cap5);
 		const bool front = s < 0.0f;
-		tIn[j] = front ? t : -inf;
-		tOut[j] = front ? inf : t;
+		if (front & !cap) tHit = fmaxf(tHit, t);
+		if (front & cap) tLow = fmaxf(tLow, t);
+		if (!front) tBound = fminf(tBound, t);
 	}
-	const float tLow = fmaxf(cap4 ? tIn[4] : -inf, cap5 ? tIn[5] : -inf);
-	const float tHit = fmaxf(fmaxf(fmaxf(tIn[0], tIn[1]), fmaxf(tIn[2], tIn[3])), fmaxf(cap4 ? -inf : tIn[4], cap5 ? -inf : tIn[5]));
-	const float tBound = fminf(fminf(fminf(tOut[0], tOut[1]), fminf(tOut[2], tOut[3])), fminf(tOut[4], tOut[5]));
 	return (tHit <= tBound) & (tHit >= 0.0f) & (tHit >= tLow) & (tHit < tMax);
 }
 
