@@ -34,7 +34,7 @@ UNIT = "Mrays/s"
 # 6.45 triangle tests, 0.54 light tests, 0.46 light samples, 0.86 hemisphere samples, 0.36 BRDF evals per ray
 FLOP_PER_RAY = 937.0
 BYTES_PER_RAY = 1430.0
-NCU_DRAM_BYTES_PER_LAUNCH = 135424 + 14864896
+NCU_DRAM_BYTES_PER_LAUNCH = 191744 + 12758272
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x FP32 lanes x 2 (FMA) x max SM clock
 
 
@@ -316,7 +316,7 @@ def main():
         roofline = {
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the ncu --set full
-            # capture profiles/r01_v23_cornell256_ncu_summary.txt (0.14 MB read + 14.9 MB written: the part of the 61 MB chunk-sum scratch
+            # capture profiles/r01_v34_cornell256_ncu_summary.txt (0.19 MB read + 12.8 MB written: the part of the 61 MB chunk-sum scratch
             # that left the L2 during the cold, serialised ncu pass; the scene tables never leave the SMs)
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.spp == SPP and world == 1 and precision == fb.FP32) else None,
             "peak_source": "FFMA micro-benchmark run in this process (fray_gpu_measure_peaks); MEASURED_PEAKS.json holds no FP32 figure",
