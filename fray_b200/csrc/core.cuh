@@ -270,6 +270,8 @@ template <typename R> struct DScene {
 	int numFlatTotal;          // records in flatPolys including the shadow sets (what the kernels stage)
 	int numFlatSpheres;        // (centre, R^2) vectors that follow the records in flatPolys; their FlatInfo follow the lights'
 	int numFlatHex;            // convex hexahedra (FRAY_HEX_VEC vectors each) after the spheres; FlatInfo of their faces after the spheres'
+	int numFlat2;              // two-sided records (FRAY_FLAT_POLY_VEC vectors each) after the hexahedra; one FlatInfo each, after the hexahedron faces'
+	int flat2InfoBase;         // FlatInfo index of the first two-sided record
 	int numFlatInfo;           // all FlatInfo entries
 	unsigned shadowHex[FRAY_SHADOW_LIGHTS]; // bit k: hexahedron k can occlude a ray towards light l
 };
@@ -816,6 +818,7 @@ template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
 #define FRAY_F_SPHERES 32 // the flat table has a sphere list
 #define FRAY_F_HEX 64     // the flat table has convex hexahedra
 #define FRAY_F_LENS 128   // the camera uses depth of field or stereo
+#define FRAY_F_TWOSIDED 256 // the flat table has a list of two-sided records (the untextured variants beyond the lean one)
 #define FRAY_F_GENERIC (FRAY_F_NODES | FRAY_F_TEX | FRAY_F_LENS)
 
 // The kernel variants compiled per precision, smallest first; a scene runs on the first one that covers its feature bits.
@@ -827,11 +830,11 @@ template <> struct Variants<float> {
 	static constexpr int mask(int i)
 	{
 		return i == 0 ? kLean                                                      // brute-force meshes, planes, lights (cornell_box)
-		     : i == 1 ? (kLean | FRAY_F_SPHERES)                                     // + translated spheres (smallpt)
+		     : i == 1 ? (kLean | FRAY_F_SPHERES | FRAY_F_TWOSIDED)                   // + translated spheres, two-sided polygons (smallpt)
 		     : i == 2 ? (FRAY_F_FLAT | FRAY_F_ATTR | FRAY_F_TEX | FRAY_F_LENS)       // textured brute-force meshes and planes, any camera (zaphod)
-		     : i == 3 ? (kLean | FRAY_F_SPHERES | FRAY_F_NODES)                      // + KD meshes / other primitives, untextured
+		     : i == 3 ? (kLean | FRAY_F_SPHERES | FRAY_F_NODES | FRAY_F_TWOSIDED)    // + KD meshes / other primitives, untextured
 		     : i == 4 ? kAll                                                         // everything but CSG
-		              : (kAll | FRAY_F_CSG);
+		              : (kAll | FRAY_F_CSG | FRAY_F_TWOSIDED);                       // the fallback for every combination (e.g. a lens added later to a scene with a two-sided list)
 	}
 };
 template <> struct Variants<double> {
@@ -845,6 +848,7 @@ struct FlatTab {
 	const FlatInfo* info;
 	const float4* spheres;
 	const float4* hexes;
+	const float4* polys2; // two-sided records
 };
 
 // Node::intersect, src/geometry.cpp:196-208. On success h is in WORLD space (ip, norm, dist).
@@ -908,6 +912,7 @@ template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const
 			if (flatHexAny(ft.hexes, sc.numFlatHex, hexMask, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 		}
 		if ((F & FRAY_F_SPHERES) && flatSpheresAny(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		if ((F & FRAY_F_TWOSIDED) && flatAny2(ft.polys2, sc.numFlat2, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 	}
 	if (F & FRAY_F_NODES) {
 		for (int n = 0; n < sc.numNodes; n++) {
@@ -959,6 +964,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 		flatClosest(ft.polys, sc.numFlatAll, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
 		if (F & FRAY_F_HEX) flatHexClosest(ft.hexes, sc.numFlatHex, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
 		if (F & FRAY_F_SPHERES) flatSpheresClosest(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx, sc.numFlatAll);
+		if (F & FRAY_F_TWOSIDED) flatClosest2(ft.polys2, sc.numFlat2, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx, sc.flat2InfoBase);
 		if (idx >= 0) {
 			const FlatInfo& fi = ft.info[idx];
 			if (fi.flags & FRAY_FLAT_LIGHT) {

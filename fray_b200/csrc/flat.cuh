@@ -116,6 +116,50 @@ FRAY_HD bool flatAny(const float4* __restrict__ P, int n, float ox, float oy, fl
 	return hit;
 }
 
+// ---- two-sided records -----------------------------------------------------------------------------------------------
+// Polygons that are hit from either side -- Plane primitives (src/geometry.cpp:30-50) and the triangles of meshes without
+// back-face culling -- live in a list of their own: one record per polygon instead of a front and a back copy, tested without
+// the front-side term (t = h / s has the right sign whichever way the ray crosses the plane).
+FRAY_HD float flatTest2(const float4* __restrict__ rec, float ox, float oy, float oz, float dx, float dy, float dz, float& t)
+{
+	const float4 pl = rec[0], e0 = rec[1], e1 = rec[2], e2 = rec[3], e3 = rec[4];
+	const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, pl.z * dz));
+	const float h = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
+	t = flatDivide(h, s);
+	const float px = fmaf(dx, t, ox), py = fmaf(dy, t, oy), pz = fmaf(dz, t, oz);
+	const float a = fmaf(e0.x, px, fmaf(e0.y, py, fmaf(e0.z, pz, e0.w)));
+	const float b = fmaf(e1.x, px, fmaf(e1.y, py, fmaf(e1.z, pz, e1.w)));
+	const float c = fmaf(e2.x, px, fmaf(e2.y, py, fmaf(e2.z, pz, e2.w)));
+	const float e = fmaf(e3.x, px, fmaf(e3.y, py, fmaf(e3.z, pz, e3.w)));
+	return fminf(fminf(fminf(a, b), c), fminf(e, t));
+}
+
+FRAY_HD void flatClosest2(const float4* __restrict__ P, int n, float ox, float oy, float oz, float dx, float dy, float dz, float& tBest, int& idx, int idxBase)
+{
+#if defined(__CUDACC__)
+#pragma unroll 2
+#endif
+	for (int i = 0; i < n; i++) {
+		float t;
+		const bool ok = (flatTest2(P + FRAY_FLAT_POLY_VEC * i, ox, oy, oz, dx, dy, dz, t) >= 0.0f) & (t < tBest);
+		tBest = ok ? t : tBest;
+		idx = ok ? idxBase + i : idx;
+	}
+}
+
+FRAY_HD bool flatAny2(const float4* __restrict__ P, int n, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
+{
+	bool hit = false;
+#if defined(__CUDACC__)
+#pragma unroll 2
+#endif
+	for (int i = 0; i < n; i++) {
+		float t;
+		hit |= (flatTest2(P + FRAY_FLAT_POLY_VEC * i, ox, oy, oz, dx, dy, dz, t) >= 0.0f) & (t < tMax);
+	}
+	return hit;
+}
+
 // ---- spheres ---------------------------------------------------------------------------------------------------------
 // Sphere::intersect (src/geometry.cpp:52-83) for sphere nodes whose transform is a pure translation, as world-space
 // (centre, R^2) records walked like the polygon records. Nearest non-negative root, the far one from inside; evaluated in the

@@ -82,11 +82,12 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 {
 	extern __shared__ float4 flatSmem[];
 	FlatTab ft;
-	// layout: records (incl. shadow sets) | spheres | hexahedra | FlatInfo (records, lights, spheres, hexahedron faces)
-	const int nVec = FRAY_FLAT_POLY_VEC * sc.numFlatTotal + sc.numFlatSpheres + FRAY_HEX_VEC * sc.numFlatHex;
+	// layout: records (incl. shadow sets) | spheres | hexahedra | two-sided records | FlatInfo (records, lights, spheres, hexahedron faces, two-sided records)
+	const int nVec = FRAY_FLAT_POLY_VEC * (sc.numFlatTotal + sc.numFlat2) + sc.numFlatSpheres + FRAY_HEX_VEC * sc.numFlatHex;
 	ft.polys = flatSmem;
 	ft.spheres = flatSmem + FRAY_FLAT_POLY_VEC * sc.numFlatTotal;
 	ft.hexes = ft.spheres + sc.numFlatSpheres;
+	ft.polys2 = ft.hexes + FRAY_HEX_VEC * sc.numFlatHex;
 	ft.info = reinterpret_cast<const FlatInfo*>(flatSmem + nVec);
 	if (F & FRAY_F_FLAT) {
 		const int nInfo = (int) (sizeof(FlatInfo) / sizeof(float4)) * sc.numFlatInfo;
@@ -301,7 +302,7 @@ struct LaunchConfig {
 
 template <typename R> inline size_t flatSmemBytes(const DScene<R>& sc)
 {
-	return ((size_t) sc.numFlatTotal * FRAY_FLAT_POLY_VEC + sc.numFlatSpheres + (size_t) sc.numFlatHex * FRAY_HEX_VEC) * sizeof(float4) + (size_t) sc.numFlatInfo * sizeof(FlatInfo);
+	return ((size_t) (sc.numFlatTotal + sc.numFlat2) * FRAY_FLAT_POLY_VEC + sc.numFlatSpheres + (size_t) sc.numFlatHex * FRAY_HEX_VEC) * sizeof(float4) + (size_t) sc.numFlatInfo * sizeof(FlatInfo);
 }
 
 // one launch of the render (or AOV) kernel for precision R; defined in render_fp32.cu / render_fp64.cu

@@ -126,8 +126,21 @@ template <typename R> struct SceneImage {
 	std::vector<float4> flatPolys;
 	std::vector<FlatInfo> flatInfo;
 
+	std::vector<float4> flat2Polys; // two-sided records (flat.cuh): one record and one FlatInfo per polygon
+	std::vector<FlatInfo> flat2Info;
+
+	// Two-sided polygons go to the list of their own in the untextured kernel variants (smallpt: six Plane primitives, 12 -> 6
+	// records per ray); the textured variants keep a front and a back copy in the main list -- their kernels are at the register
+	// limit and lost more to the extra loops than the shorter table gave (zaphod 1.55 -> 1.75 ms)
+	bool twoSidedList = false; // set by build() before buildFlat
+
 	void pushFlat(const float4 rec[5], const FlatInfo& fi, bool twoSided)
 	{
+		if (twoSided && twoSidedList) {
+			for (int k = 0; k < 5; k++) flat2Polys.push_back(rec[k]);
+			flat2Info.push_back(fi);
+			return;
+		}
 		for (int k = 0; k < 5; k++) flatPolys.push_back(rec[k]);
 		flatInfo.push_back(fi);
 		if (twoSided) { // the same polygon seen from behind: plane reversed, edges unchanged
@@ -300,6 +313,8 @@ template <typename R> struct SceneImage {
 	{
 		flatPolys.clear();
 		flatInfo.clear();
+		flat2Polys.clear();
+		flat2Info.clear();
 		int feat = 0;
 		const float4 always = plane4(D3{ 0, 0, 0 }, 1.0);
 		int numRect = 0;
@@ -316,7 +331,7 @@ template <typename R> struct SceneImage {
 			if (g.type == FRAY_GEOM_PLANE) {
 				// Plane::intersect, src/geometry.cpp:30-50: the square |x|, |z| <= limit of the object-space plane y = height, hit
 				// from either side, normal always +y. Under the node transform that is a world-space parallelogram: two records.
-				if (room < 2) continue;
+				if (room < (twoSidedList ? 1 : 2)) continue;
 				const double height = g.p[0], limit = g.p[1];
 				const double* I = n.T.inv;
 				const D3 off{ n.T.offset[0], n.T.offset[1], n.T.offset[2] };
@@ -343,7 +358,7 @@ template <typename R> struct SceneImage {
 				const bool attr = nodes[ni].needsUV || n.bump >= 0;
 				fi.node = ni; fi.tri0 = fi.tri1 = -1; fi.mesh = -1; fi.flags = attr ? (FRAY_FLAT_ATTR | FRAY_FLAT_PLANE) : 0;
 				pushFlat(rec, fi, true);
-				room -= 2;
+				room -= twoSidedList ? 1 : 2;
 				nodes[ni].inFlat = 1;
 				feat |= FRAY_F_FLAT;
 				if (attr) feat |= FRAY_F_ATTR;
@@ -464,7 +479,7 @@ template <typename R> struct SceneImage {
 				mine.push_back(cd);
 				if (merged) t++;
 			}
-			const int count = (int) mine.size() * (cull ? 1 : 2);
+			const int count = (int) mine.size() * ((cull || twoSidedList) ? 1 : 2);
 			if (count > room) continue;
 			room -= count;
 			cands.insert(cands.end(), mine.begin(), mine.end());
@@ -551,6 +566,12 @@ template <typename R> struct SceneImage {
 			}
 			feat |= FRAY_F_HEX;
 		}
+		// two-sided records: after the hexahedra, their FlatInfo after the hexahedron faces'
+		offsets.numFlat2 = (int) flat2Info.size();
+		offsets.flat2InfoBase = (int) flatInfo.size();
+		flatPolys.insert(flatPolys.end(), flat2Polys.begin(), flat2Polys.end());
+		flatInfo.insert(flatInfo.end(), flat2Info.begin(), flat2Info.end());
+		if (offsets.numFlat2 > 0) feat |= FRAY_F_TWOSIDED;
 		offsets.numFlatInfo = (int) flatInfo.size();
 		for (FlatInfo& fi: flatInfo) {
 			if (fi.flags & FRAY_FLAT_LIGHT) continue;
@@ -561,8 +582,8 @@ template <typename R> struct SceneImage {
 			fi.shade.y = c[0]; fi.shade.z = c[1]; fi.shade.w = c[2];
 		}
 		if (getenv("FRAY_GPU_VERBOSE")) {
-			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d light records, %d spheres, %d convex hexahedra", offsets.numFlatGeom,
-			        offsets.numFlatAll - offsets.numFlatGeom, offsets.numFlatSpheres, offsets.numFlatHex);
+			fprintf(stderr, "fray_gpu: flat table: %d geometry records, %d two-sided records, %d light records, %d spheres, %d convex hexahedra", offsets.numFlatGeom,
+			        offsets.numFlat2, offsets.numFlatAll - offsets.numFlatGeom, offsets.numFlatSpheres, offsets.numFlatHex);
 			for (int l = 0; l < s.num_lights && l < FRAY_SHADOW_LIGHTS; l++)
 				if (offsets.shadowCount[l] >= 0) fprintf(stderr, ", shadow set of light %d: %d", l, offsets.shadowCount[l]);
 			fprintf(stderr, "\n");
@@ -801,8 +822,24 @@ template <typename R> struct SceneImage {
 			if (s.nodes[i].bump >= 0) features |= FRAY_F_TEX;
 		if (s.camera.dof || s.camera.stereo_separation > 0) features |= FRAY_F_LENS;
 		if (!Num<R>::kExact) {
-			features |= buildFlat(s, nodes);
-			if (!offsets.lightsInFlat) features |= FRAY_F_NODES; // the generic light loop is compiled with the generic node loop
+			// first with front and back copies of two-sided polygons; if the scene then fits the untextured variants, which have the
+			// loops for the two-sided list, once more with that list
+			auto flatFeatures = [&]() {
+				int f = buildFlat(s, nodes);
+				if (!offsets.lightsInFlat) f |= FRAY_F_NODES; // the generic light loop is compiled with the generic node loop
+				for (int i = 0; i < s.num_nodes; i++)
+					if (!nodes[i].inFlat) f |= FRAY_F_NODES;
+				return f;
+			};
+			twoSidedList = false;
+			int f = flatFeatures();
+			const int untextured = Variants<float>::kLean | FRAY_F_SPHERES | FRAY_F_NODES;
+			if (((features | f) & ~untextured) == 0 && !getenv("FRAY_GPU_NO_TWOSIDED_LIST")) {
+				for (int i = 0; i < s.num_nodes; i++) nodes[i].inFlat = 0;
+				twoSidedList = true;
+				f = flatFeatures();
+			}
+			features |= f;
 		}
 		for (int i = 0; i < s.num_nodes; i++)
 			if (!nodes[i].inFlat) features |= FRAY_F_NODES;

@@ -75,6 +75,7 @@ static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out
 	ft.info = sc.flatInfo;
 	ft.spheres = sc.flatPolys + FRAY_FLAT_POLY_VEC * sc.numFlatTotal;
 	ft.hexes = ft.spheres + sc.numFlatSpheres;
+	ft.polys2 = ft.hexes + FRAY_HEX_VEC * sc.numFlatHex;
 	const int need = img.features;
 	auto run = [&]() { // the same variant selection as VariantDispatch in render_kernels.cuh
 		if (Variants<R>::count > 0 && (need & ~Variants<R>::mask(0)) == 0) renderRows<R, Variants<R>::mask(0)>(sc, ft, *fr, W, H, spp, s0, s1, out, nextRow, total);

@@ -170,6 +170,26 @@ def test_camera_update(scenes, golden_cases):
     ctx.close()
 
 
+def test_lens_added_to_a_scene_with_a_two_sided_list(scenes, golden_cases):
+    """smallpt runs on an untextured kernel variant with its Plane primitives in the two-sided record list; switching depth
+    of field on through update_camera needs a variant with a lens AND that list -- the full fallback variant. Both precisions
+    must still agree (same seeds, path traced)."""
+    path, seed = golden_scene(golden_cases, "smallpt")
+    sc = fb.Scene(path)
+    cam = sc.move_camera()
+    cam.dof, cam.aperture_size, cam.focal_plane_dist, cam.num_dof_samples = 1, 0.8, 180.0, 8
+    imgs = {}
+    for precision in (fb.FP64, fb.FP32):
+        ctx = fb.GpuContext(sc, 0, precision)
+        sharp, _ = ctx.render(seed=seed, spp=8)
+        ctx.update_camera(cam)
+        imgs[precision], _ = ctx.render(seed=seed, spp=8)
+        assert np.isfinite(imgs[precision]).all() and not np.array_equal(sharp, imgs[precision])
+        ctx.close()
+    frac, rmse, mx = ou.compare(imgs[fb.FP64], imgs[fb.FP32], 1e-3)
+    assert rmse < 0.03, (frac, rmse, mx)
+
+
 def test_full_size_properties_cornell(data_dir):
     """BASELINE.json configs[2] at its full size: size-independent properties instead of a CPU image.
     (a) tiles + sample ranges add up, (b) the 256-spp image is the mean of two independent 128-spp halves, (c) energy is
