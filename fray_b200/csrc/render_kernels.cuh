@@ -117,7 +117,7 @@ template <> struct RenderRng<true> {
 };
 
 template <typename R, bool GI, int F>
-__global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? ((F == Variants<float>::kLean) ? 7 : 6) : ((F & FRAY_F_NODES) ? FRAY_WHITTED_KD_CTAS : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
+__global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F_NODES | FRAY_F_TEX)) == 0) ? 7 : 6) : ((F & FRAY_F_NODES) ? FRAY_WHITTED_KD_CTAS : 4))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
