@@ -10,7 +10,8 @@
 //     writes the chunk's sum and takes the next item. Items come from a warp-level pool (a contiguous id range in uniform
 //     registers; lanes that need one agree by __ballot_sync + popc) which lane 0 refills 32 ids at a time with ONE atomicAdd
 //     on the global counter. No lane ever waits for another lane's path, pixel or tile; the only drain is at the very end
-//     of the kernel, and it is bounded by one item (C is chosen so that a lane sees >= ~12 items per call);
+//     of the kernel, and it is bounded by one item (C is chosen so that a lane sees >= ~32 items per call). A refill decodes
+//     its batch -- one tile, one chunk -- with all 32 lanes and parks the items in shared memory, so taking one is two LDS;
 //   * a chunk's sum is accumulated in sample order by one lane; chunk sums go to a scratch buffer and combineKernel adds
 //     them per pixel in chunk order (with one chunk per pixel the lane writes the pixel directly). A pixel is therefore a pure
 //     function of (scene, seed, sample range, C): no float atomics, run-to-run bit-identical.
