@@ -47,6 +47,14 @@ def main():
     extra = os.path.join(scenes.DATA_DIR, "flat_transforms__test.fray")
     shutil.copyfile(os.path.join(ROOT, "tests", "scenes", "flat_transforms.fray"), extra)
     todo.append((extra, 7))
+    # the open tubes (convex solids with two cap planes) of tests/test_flat_table.py
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_flat_table import OPEN_TUBE_OBJ
+    with open(os.path.join(scenes.DATA_DIR, "geom", "open_tube__test.obj"), "w") as f:
+        f.write(OPEN_TUBE_OBJ)
+    tube = os.path.join(scenes.DATA_DIR, "open_tube__test.fray")
+    shutil.copyfile(os.path.join(ROOT, "tests", "scenes", "open_tube.fray"), tube)
+    todo.append((tube, 5))
     for path, seed in todo:
         sc = fb.Scene(path)
         for precision in (fb.FP32, fb.FP64):
