@@ -27,6 +27,7 @@ RENDER_BEAUTY = 0
 RENDER_AOV = 1
 FRAME_SUM = 1
 FRAME_OWNED_ONLY = 2
+FRAME_SAMPLE_RANGE = 4
 
 
 class FraySettings(C.Structure):  # FrayGpuSettings
@@ -201,8 +202,11 @@ class Scene:
             i += 1
 
 
-def make_frame(spp=0, seed=42, sample_begin=0, sample_end=0, bucket_rank=0, bucket_count=0, mode=RENDER_BEAUTY, flags=0) -> FrayFrame:
-    return FrayFrame(spp, seed, sample_begin, sample_end, bucket_rank, bucket_count, mode, flags)
+def make_frame(spp=0, seed=42, sample_begin=None, sample_end=None, bucket_rank=0, bucket_count=0, mode=RENDER_BEAUTY, flags=0) -> FrayFrame:
+    """A FrayGpuFrame. A sample range given explicitly is literal (FRAME_SAMPLE_RANGE): begin == end is an empty share."""
+    if sample_begin is not None or sample_end is not None:
+        flags |= FRAME_SAMPLE_RANGE
+    return FrayFrame(spp, seed, sample_begin or 0, sample_end or 0, bucket_rank, bucket_count, mode, flags)
 
 
 class GpuContext:

@@ -26,6 +26,10 @@
 
 namespace fray {
 
+#if defined(FRAY_DEBUG_TRACE) && !defined(__CUDA_ARCH__)
+extern thread_local int g_frayTrace; // tests/emul: print the rays of one pixel
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // numeric traits
 // ---------------------------------------------------------------------------------------------------
@@ -38,6 +42,7 @@ template <> struct Num<double> {
 	FRAY_HD static double offsetEps(double /*magnitude*/) { return 1e-6; }
 	FRAY_HD static double reshootEps(double /*magnitude*/) { return 1e-6; }
 	FRAY_HD static double slackEps(double /*magnitude*/) { return 1e-6; }
+	FRAY_HD static double selfEps(double /*magnitude*/) { return 0; } // parity precision keeps the reference's rules literally
 	FRAY_HD static double rcpLen(double s) { return 1.0 / sqrt(s); }
 	FRAY_HD static double sqrtR(double s) { return sqrt(s); }
 	FRAY_HD static double powR(double a, double b) { return pow(a, b); }
@@ -68,6 +73,11 @@ template <> struct Num<float> {
 	FRAY_HD static float offsetEps(float magnitude) { return fmaxf(1e-6f, magnitude * FRAY_F32_OFFSET_SCALE); }
 	FRAY_HD static float reshootEps(float magnitude) { return fmaxf(1e-6f, magnitude * FRAY_F32_RESHOOT_SCALE); }
 	FRAY_HD static float slackEps(float magnitude) { return fmaxf(1e-6f, magnitude * FRAY_F32_SLACK_SCALE); }
+	// A ray that starts ON a closed surface (a secondary ray: its origin is a hit point moved by offsetEps) meets that same
+	// surface again at a parameter of the order of the rounding error of the hit point, with either sign. Crossings of the
+	// ORIGIN'S OWN node below this bound are not hits (see intersectSphere / intersectCube / csgCrossings); the bound is a few
+	// times the offset, far below any chord the scene can show at FP32 resolution.
+	FRAY_HD static float selfEps(float magnitude) { return fmaxf(1e-5f, magnitude * 3e-5f); }
 	FRAY_HD static float rcpLen(float s)
 	{
 #if defined(__CUDA_ARCH__)
@@ -355,7 +365,8 @@ template <typename R> FRAY_HD bool intersectPlane(const DGeom<R>& g, const Ray<R
 }
 
 // Sphere::intersect, src/geometry.cpp:52-83
-template <typename R> FRAY_HD bool intersectSphere(const DGeom<R>& g, const Ray<R>& ray, Hit<R>& h, bool needUV)
+// `self` (fast precision): the ray starts on this very sphere -- only the far crossing can be a hit
+template <typename R> FRAY_HD bool intersectSphere(const DGeom<R>& g, const Ray<R>& ray, Hit<R>& h, bool needUV, bool self = false)
 {
 	const V3<R> O(g.p[0], g.p[1], g.p[2]);
 	const R Rad = g.p[3];
@@ -382,8 +393,13 @@ template <typename R> FRAY_HD bool intersectSphere(const DGeom<R>& g, const Ray<
 		const R q = b + (b < 0 ? -Num<R>::sqrtR(disc) : Num<R>::sqrtR(disc));
 		const R p1 = q, p2 = (q != 0) ? c / q : 0;
 		const R smaller = fmin(p1, p2), larger = fmax(p1, p2);
-		if (larger < 0) return false;
-		d = (smaller >= 0) ? smaller : larger;
+		if (self) {
+			if (!(larger > Num<R>::selfEps(fmax(maxAbs(ray.start), Rad)))) return false;
+			d = larger;
+		} else {
+			if (larger < 0) return false;
+			d = (smaller >= 0) ? smaller : larger;
+		}
 	}
 	h.ip = ray.start + ray.dir * d;
 	h.dist = dist3(ray.start, h.ip);
@@ -400,11 +416,12 @@ template <typename R> FRAY_HD bool intersectSphere(const DGeom<R>& g, const Ray<
 }
 
 // Cube::intersect + intersectCubeSide, src/geometry.cpp:85-137
-template <typename R> FRAY_HD bool intersectCube(const DGeom<R>& g, const Ray<R>& ray, Hit<R>& h)
+template <typename R> FRAY_HD bool intersectCube(const DGeom<R>& g, const Ray<R>& ray, Hit<R>& h, bool self = false)
 {
 	const V3<R> O(g.p[0], g.p[1], g.p[2]);
 	const R hs = g.p[3];
 	const R slack = Num<R>::slackEps(maxAbs(O) + hs);
+	const R tMin = self ? Num<R>::selfEps(maxAbs(O) + hs) : (R) 0; // a ray that starts on this cube cannot hit the face it leaves
 	R best = (R) 1e30;
 	bool found = false;
 #if defined(__CUDACC__)
@@ -417,7 +434,7 @@ template <typename R> FRAY_HD bool intersectCube(const DGeom<R>& g, const Ray<R>
 		const R target = O.get(axis) + sgn * hs;
 		if (fabs(dir) < (R) 1e-9) continue;
 		const R mult = (target - start) / dir;
-		if (mult < 0) continue;
+		if (mult < tMin) continue;
 		const V3<R> ip = ray.start + ray.dir * mult;
 		if (ip.x < O.x - hs - slack || ip.x > O.x + hs + slack) continue;
 		if (ip.y < O.y - hs - slack || ip.y > O.y + hs + slack) continue;
@@ -719,14 +736,14 @@ FRAY_HD_HOT bool intersectMeshFast(const DScene<float>& sc, int meshIdx, const R
 
 // geometry dispatch without CSG (the leaves of a CSG tree and plain nodes)
 template <typename R, bool ANYHIT>
-FRAY_HD bool intersectLeafGeom(const DScene<R>& sc, int gi, const Ray<R>& ray, R maxT, Hit<R>& h, bool needUV, bool needAttr)
+FRAY_HD bool intersectLeafGeom(const DScene<R>& sc, int gi, const Ray<R>& ray, R maxT, Hit<R>& h, bool needUV, bool needAttr, bool self = false)
 {
 	const DGeom<R>& g = sc.geoms[gi];
 	bool ok;
 	switch (g.type) {
 		case FRAY_GEOM_PLANE: ok = intersectPlane(g, ray, h); break;
-		case FRAY_GEOM_SPHERE: ok = intersectSphere(g, ray, h, needUV); break;
-		case FRAY_GEOM_CUBE: ok = intersectCube(g, ray, h); break;
+		case FRAY_GEOM_SPHERE: ok = intersectSphere(g, ray, h, needUV, self); break;
+		case FRAY_GEOM_CUBE: ok = intersectCube(g, ray, h, self); break;
 		case FRAY_GEOM_MESH:
 			if constexpr (Num<R>::kExact) ok = intersectMesh<R, ANYHIT>(sc, g.mesh, ray, maxT, h);
 			else ok = intersectMeshFast<ANYHIT>(sc, g.mesh, ray, maxT, h);
@@ -753,7 +770,7 @@ template <typename R, int LEVEL>
 FRAY_HD bool intersectGeomCsg(const DScene<R>& sc, int gi, const Ray<R>& ray, Hit<R>& h)
 {
 	const int type = sc.geoms[gi].type;
-	if (type >= FRAY_GEOM_CSG_PLUS && type <= FRAY_GEOM_CSG_MINUS) return CsgEval<R, LEVEL>::run(sc, gi, ray, h);
+	if (type >= FRAY_GEOM_CSG_PLUS && type <= FRAY_GEOM_CSG_MINUS) return CsgEval<R, LEVEL>::run(sc, gi, ray, h, false);
 	return intersectLeafGeom<R, false>(sc, gi, ray, Num<R>::big(), h, true, true);
 }
 
@@ -775,19 +792,177 @@ FRAY_HD_COLD int csgAllHits(const DScene<R>& sc, int gi, const Ray<R>& rayIn, Cs
 	return n;
 }
 
+// ---- fast precision: every boundary crossing of a geometry along the ray, ascending ---------------------------------------
+// findAllIntersections (src/geometry.cpp:139-157) restarts the ray 1e-6 behind every hit. In FP32 a restarted ray sits within
+// rounding error of the surface it just left and meets it again (a sphere answers 17.3754501 and then 17.3754520), the parity of
+// the hit count flips and CsgOp::intersect (:159-194) reports the wrong side. So the crossings are enumerated from the ORIGINAL
+// ray instead: both roots of a sphere, entry and exit of a cube, the one crossing of a plane, and for an operand that is itself
+// a CSG every change of its inside state. Same lists as the reference's in exact arithmetic. `tMin`: crossings below it are
+// dropped -- zero for an ordinary ray, selfEps for a ray that starts on this very node, whose own surface passes through its
+// origin (the inside state then follows from the crossings AHEAD, i.e. it is that of the side the ray travels into, which is the
+// side the reference's 1e-6 offset puts it on).
+template <int LEVEL> struct CsgCross {
+	static FRAY_HD_COLD int run(const DScene<float>& sc, int gi, const Ray<float>& ray, float tMin, CsgHit<float>* out);
+};
+template <> struct CsgCross<FRAY_GPU_MAX_CSG_DEPTH + 1> {
+	static FRAY_HD int run(const DScene<float>&, int, const Ray<float>&, float, CsgHit<float>*) { return 0; }
+};
+
+FRAY_HD bool csgOp(int type, bool a, bool b)
+{
+	return type == FRAY_GEOM_CSG_PLUS ? (a || b) : (type == FRAY_GEOM_CSG_AND ? (a && b) : (a && !b));
+}
+
+template <int LEVEL>
+FRAY_HD_COLD int CsgCross<LEVEL>::run(const DScene<float>& sc, int gi, const Ray<float>& ray, float tMin, CsgHit<float>* out)
+{
+	const DGeom<float>& g = sc.geoms[gi];
+	int n = 0;
+	auto put = [&](float t, const V3<float>& ip, const V3<float>& norm, float u, float v) {
+		CsgHit<float>& c = out[n++];
+		c.dist = t; c.ip = ip; c.norm = norm; c.u = u; c.v = v; c.tri = -1; c.mesh = -1; c.geom = gi;
+	};
+	switch (g.type) {
+		case FRAY_GEOM_SPHERE: { // Sphere::intersect, src/geometry.cpp:52-83: both roots, cancellation-free (see intersectSphere)
+			const V3<float> O(g.p[0], g.p[1], g.p[2]);
+			const float Rad = g.p[3];
+			const V3<float> H = ray.start - O;
+			const float b = -dot(ray.dir, H);
+			const V3<float> perp = H + ray.dir * b;
+			const float disc = Rad * Rad - lengthSqr(perp);
+			if (disc < 0) return 0;
+			const float c = lengthSqr(H) - Rad * Rad;
+			const float sq = sqrtf(disc);
+			const float q = b + (b < 0 ? -sq : sq);
+			const float p1 = q, p2 = (q != 0) ? c / q : 0;
+			const float roots[2] = { fminf(p1, p2), fmaxf(p1, p2) };
+			for (int k = 0; k < 2; k++) {
+				if (!(roots[k] >= tMin)) continue;
+				const V3<float> ip = ray.start + ray.dir * roots[k];
+				const V3<float> nn = normalized(ip - O);
+				put(roots[k], ip, nn, (float) ((atan2f(nn.z, nn.x) / (float) FRAY_PI * 180 + 180) / 360), (float) (1 - (asinf(nn.y) / (float) FRAY_PI * 180 + 90) / 180));
+			}
+			return n;
+		}
+		case FRAY_GEOM_CUBE: { // Cube::intersect, src/geometry.cpp:85-137, as three slabs: entry = latest near plane, exit = earliest far plane
+			const V3<float> O(g.p[0], g.p[1], g.p[2]);
+			const float hs = g.p[3];
+			float tIn = -FLT_MAX, tOut = FLT_MAX;
+			int aIn = 0, aOut = 0;
+			float sIn = 0, sOut = 0;
+			for (int axis = 0; axis < 3; axis++) {
+				const float s = ray.start.get(axis), d = ray.dir.get(axis), c = O.get(axis);
+				if (fabsf(d) < 1e-9f) { // parallel to the slab (src/geometry.cpp:110): inside it or never
+					if (s < c - hs || s > c + hs) return 0;
+					continue;
+				}
+				const float r = 1.0f / d;
+				const float tLo = (c - hs - s) * r, tHi = (c + hs - s) * r;
+				const float tn = fminf(tLo, tHi), tf = fmaxf(tLo, tHi);
+				if (tn > tIn) { tIn = tn; aIn = axis; sIn = d > 0 ? -1.0f : 1.0f; }
+				if (tf < tOut) { tOut = tf; aOut = axis; sOut = d > 0 ? 1.0f : -1.0f; }
+			}
+			if (!(tIn <= tOut)) return 0;
+			for (int k = 0; k < 2; k++) {
+				const float t = k == 0 ? tIn : tOut;
+				const int axis = k == 0 ? aIn : aOut;
+				const float sgn = k == 0 ? sIn : sOut;
+				if (!(t >= tMin)) continue;
+				const V3<float> ip = ray.start + ray.dir * t;
+				const V3<float> nn(axis == 0 ? sgn : 0, axis == 1 ? sgn : 0, axis == 2 ? sgn : 0);
+				put(t, ip, nn, axis == 0 ? ip.y : ip.x, axis == 2 ? ip.y : ip.z);
+			}
+			return n;
+		}
+		case FRAY_GEOM_PLANE: {
+			Hit<float> h;
+			if (intersectPlane(g, ray, h) && h.dist >= tMin) put(h.dist, h.ip, h.norm, h.u, h.v);
+			return n;
+		}
+		case FRAY_GEOM_MESH: { // restart behind every hit like the reference; a re-hit within selfEps of the previous one is the same crossing
+			Ray<float> r = ray;
+			Hit<float> h;
+			float last = -FLT_MAX;
+			int counter = FRAY_CSG_MAX_HITS;
+			while (n < FRAY_CSG_MAX_HITS && counter-- > 0 && intersectLeafGeom<float, false>(sc, gi, r, Num<float>::big(), h, true, true)) {
+				const float t = dist3(h.ip, ray.start);
+				const float sep = Num<float>::selfEps(maxAbs(h.ip));
+				if (t >= tMin && t > last + sep) {
+					CsgHit<float>& c = out[n++];
+					c.dist = t; c.ip = h.ip; c.norm = h.norm; c.u = h.u; c.v = h.v; c.tri = h.tri; c.mesh = h.mesh; c.geom = gi;
+					last = t;
+				}
+				r.start = h.ip + r.dir * Num<float>::reshootEps(maxAbs(h.ip));
+			}
+			return n;
+		}
+		default: { // CsgOp::intersect, src/geometry.cpp:159-194, carried on past the first change of state
+			if (g.type < FRAY_GEOM_CSG_PLUS || g.type > FRAY_GEOM_CSG_MINUS) return 0;
+			CsgHit<float> L[FRAY_CSG_MAX_HITS], Rr[FRAY_CSG_MAX_HITS];
+			const int nL = CsgCross<LEVEL + 1>::run(sc, g.left, ray, tMin, L);
+			const int nR = CsgCross<LEVEL + 1>::run(sc, g.right, ray, tMin, Rr);
+			bool inL = (nL & 1) == 1, inR = (nR & 1) == 1;
+#if defined(FRAY_DEBUG_TRACE) && !defined(__CUDA_ARCH__)
+			if (g_frayTrace) {
+				printf("    csg geom %d level %d: left %d crossings:", gi, LEVEL, nL);
+				for (int k = 0; k < nL; k++) printf(" %.7f", (double) L[k].dist);
+				printf(" | right %d crossings:", nR);
+				for (int k = 0; k < nR; k++) printf(" %.7f", (double) Rr[k].dist);
+				printf("\n");
+			}
+#endif
+			bool state = csgOp(g.type, inL, inR);
+			int i = 0, j = 0;
+			while ((i < nL || j < nR) && n < FRAY_CSG_MAX_HITS) {
+				const bool takeL = (j >= nR) || (i < nL && !(Rr[j].dist < L[i].dist));
+				const CsgHit<float>& c = takeL ? L[i] : Rr[j];
+				if (takeL || g.left == g.right) inL = !inL; else inR = !inR;
+				if (takeL) i++; else j++;
+				const bool now = csgOp(g.type, inL, inR);
+				if (now != state) {
+					out[n] = c;
+					out[n].geom = gi;
+					n++;
+					state = now;
+				}
+			}
+			return n;
+		}
+	}
+}
+
 template <typename R, int LEVEL> struct CsgEval {
 	// CsgOp::intersect, src/geometry.cpp:159-194 (the two hit lists are already sorted along the ray; they are merged
-	// with the left operand first on equal distance)
-	FRAY_HD_COLD static bool run(const DScene<R>& sc, int gi, const Ray<R>& ray, Hit<R>& h)
+	// with the left operand first on equal distance). `self`: the ray starts on the node this geometry belongs to.
+	FRAY_HD_COLD static bool run(const DScene<R>& sc, int gi, const Ray<R>& ray, Hit<R>& h, bool self)
 	{
 		const DGeom<R>& g = sc.geoms[gi];
+		if constexpr (!Num<R>::kExact) {
+			if (LEVEL == 0) { // the first change of state along the ray
+				CsgHit<float> X[FRAY_CSG_MAX_HITS];
+				const float tMin = self ? Num<float>::selfEps(maxAbs(ray.start)) : 0.0f;
+				if (CsgCross<0>::run(sc, gi, ray, tMin, X) == 0) return false;
+				const CsgHit<float>& c = X[0];
+				h.dist = c.dist; h.ip = c.ip; h.norm = c.norm; h.u = c.u; h.v = c.v; h.tri = c.tri; h.mesh = c.mesh;
+				h.geom = gi;
+				return true;
+			}
+		}
 		CsgHit<R> L[FRAY_CSG_MAX_HITS], Rr[FRAY_CSG_MAX_HITS];
 		const int nL = csgAllHits<R, LEVEL + 1>(sc, g.left, ray, L);
 		const int nR = csgAllHits<R, LEVEL + 1>(sc, g.right, ray, Rr);
 		bool inL = (nL & 1) == 1, inR = (nR & 1) == 1;
+#if defined(FRAY_DEBUG_TRACE) && !defined(__CUDA_ARCH__)
+		if (g_frayTrace) {
+			printf("    csg geom %d level %d: left %d hits:", gi, LEVEL, nL);
+			for (int k = 0; k < nL; k++) printf(" %.7f", (double) L[k].dist);
+			printf(" | right %d hits:", nR);
+			for (int k = 0; k < nR; k++) printf(" %.7f", (double) Rr[k].dist);
+			printf("\n");
+		}
+#endif
 		const int type = g.type;
-		auto op = [type](bool a, bool b) { return type == FRAY_GEOM_CSG_PLUS ? (a || b) : (type == FRAY_GEOM_CSG_AND ? (a && b) : (a && !b)); };
-		const bool start = op(inL, inR);
+		const bool start = csgOp(type, inL, inR);
 		int i = 0, j = 0;
 		while (i < nL || j < nR) {
 			const bool takeL = (j >= nR) || (i < nL && !(Rr[j].dist < L[i].dist));
@@ -795,7 +970,7 @@ template <typename R, int LEVEL> struct CsgEval {
 			// `if (ip.geom == left) inLeft = !inLeft; else inRight = !inRight;`
 			if (takeL || g.left == g.right) inL = !inL; else inR = !inR;
 			if (takeL) i++; else j++;
-			if (op(inL, inR) != start) {
+			if (csgOp(type, inL, inR) != start) {
 				h.dist = c.dist; h.ip = c.ip; h.norm = c.norm; h.u = c.u; h.v = c.v; h.tri = c.tri; h.mesh = c.mesh;
 				h.geom = gi;
 				return true;
@@ -805,7 +980,7 @@ template <typename R, int LEVEL> struct CsgEval {
 	}
 };
 template <typename R> struct CsgEval<R, FRAY_GPU_MAX_CSG_DEPTH> {
-	FRAY_HD static bool run(const DScene<R>&, int, const Ray<R>&, Hit<R>&) { return false; } // rejected at flatten time
+	FRAY_HD static bool run(const DScene<R>&, int, const Ray<R>&, Hit<R>&, bool) { return false; } // rejected at flatten time
 };
 
 // feature bits (template parameter F of the kernels): code paths that cost registers, local memory and instruction-cache
@@ -855,10 +1030,13 @@ struct FlatTab {
 // `maxDist` bounds the search in world units: hits farther away may be dropped (closest-hit pruning against the best
 // node so far, fast precision only; the reference compares afterwards, src/main.cpp:256) and, for ANYHIT, the mesh
 // descent stops at the first triangle within it (h then only carries dist).
+// `origin`: the node the ray starts on (a secondary or shadow ray), or -1. Fast precision uses it to tell the ray's own
+// surface from a hit (Num<float>::selfEps); parity precision ignores it.
 template <typename R, bool ANYHIT, int F>
-FRAY_HD bool intersectNode(const DScene<R>& sc, int ni, const Ray<R>& ray, R maxDist, Hit<R>& h)
+FRAY_HD bool intersectNode(const DScene<R>& sc, int ni, const Ray<R>& ray, R maxDist, Hit<R>& h, int origin = -1)
 {
 	const DNode<R>& n = sc.nodes[ni];
+	const bool self = !Num<R>::kExact && ni == origin;
 	Ray<R> local;
 	R scale = 1; // |dir * inv|: object-space ray parameter = scale * world distance
 	if (!Num<R>::kExact && n.T.identity) {
@@ -874,13 +1052,13 @@ FRAY_HD bool intersectNode(const DScene<R>& sc, int ni, const Ray<R>& ray, R max
 	const int type = sc.geoms[n.geom].type;
 	bool ok;
 	if (type >= FRAY_GEOM_CSG_PLUS && type <= FRAY_GEOM_CSG_MINUS) {
-		if (F & FRAY_F_CSG) ok = CsgEval<R, 0>::run(sc, n.geom, local, h);
+		if (F & FRAY_F_CSG) ok = CsgEval<R, 0>::run(sc, n.geom, local, h, self);
 		else ok = false;
 	} else {
 		R maxT = Num<R>::big();
 		if (ANYHIT || !Num<R>::kExact) maxT = maxDist < Num<R>::big() / 4 ? maxDist * scale * (ANYHIT ? (R) 1 : (R) 1.0001) : Num<R>::big();
-		if (ANYHIT) ok = intersectLeafGeom<R, true>(sc, n.geom, local, maxT, h, false, false);
-		else ok = intersectLeafGeom<R, false>(sc, n.geom, local, maxT, h, n.needsUV != 0, true);
+		if (ANYHIT) ok = intersectLeafGeom<R, true>(sc, n.geom, local, maxT, h, false, false, self);
+		else ok = intersectLeafGeom<R, false>(sc, n.geom, local, maxT, h, n.needsUV != 0, true, self);
 	}
 	if (!ok) return false;
 	h.ip = xfPoint(n.T, h.ip);
@@ -891,7 +1069,8 @@ FRAY_HD bool intersectNode(const DScene<R>& sc, int ni, const Ray<R>& ray, R max
 
 // visible(), src/main.cpp:64-80
 // `light`: index of the light the end point b was sampled on (selects the light's shadow set), or -1
-template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const FlatTab& ft, const V3<R>& a, const V3<R>& b, int light, RayCounters& cnt)
+// `origin`: the node the point a lies on (see intersectNode)
+template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const FlatTab& ft, const V3<R>& a, const V3<R>& b, int light, RayCounters& cnt, int origin = -1)
 {
 	cnt.rays++;
 	cnt.shadow++;
@@ -918,7 +1097,7 @@ template <typename R, int F> FRAY_HD_HOT bool visible(const DScene<R>& sc, const
 		for (int n = 0; n < sc.numNodes; n++) {
 			if ((F & FRAY_F_FLAT) && sc.nodes[n].inFlat) continue;
 			Hit<R> h;
-			if (intersectNode<R, true, F>(sc, n, ray, maxDist, h) && h.dist < maxDist) return false;
+			if (intersectNode<R, true, F>(sc, n, ray, maxDist, h, origin) && h.dist < maxDist) return false;
 		}
 	}
 	return true;
@@ -952,7 +1131,7 @@ template <typename R> FRAY_HD void flatBarycentrics(const DScene<R>& sc, const D
 
 // the two closest-hit loops of raytrace()/pathtrace(), src/main.cpp:178-199, 250-271
 template <typename R, int F>
-FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>& ray, int& node, int& light, Hit<R>& best)
+FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>& ray, int& node, int& light, Hit<R>& best, int origin = -1)
 {
 	node = -1;
 	light = -1;
@@ -1004,7 +1183,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 		for (int n = 0; n < sc.numNodes; n++) {
 			if ((F & FRAY_F_FLAT) && sc.nodes[n].inFlat) continue;
 			Hit<R> h;
-			if (intersectNode<R, false, F>(sc, n, ray, best.dist, h) && h.dist < best.dist) {
+			if (intersectNode<R, false, F>(sc, n, ray, best.dist, h, origin) && h.dist < best.dist) {
 				best = h;
 				node = n;
 				light = -1;
@@ -1162,7 +1341,7 @@ FRAY_HD void lightSample(const DLight<R>& l, RNG& rng, int sampleIdx, const V3<R
 // Whitted shading: local terms (Lambert / Phong), src/shading.cpp:48-80, 101-144
 // ---------------------------------------------------------------------------------------------------
 template <typename R, int F, typename RNG>
-FRAY_HD Col shadeDirectBody(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
+FRAY_HD Col shadeDirectBody(const DScene<R>& sc, const FlatTab& ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, int node, RNG& rng, RayCounters& cnt)
 {
 	Col diffuse = loadCol(s.color);
 	if ((F & FRAY_F_TEX) && s.texture >= 0) diffuse = diffuse * sampleTexture(sc, s.texture, rayDir, h.norm, h.u, h.v);
@@ -1183,7 +1362,7 @@ FRAY_HD Col shadeDirectBody(const DScene<R>& sc, const FlatTab& ft, const DShade
 			const float cosAngle = (float) dot(toLight, n);
 			float lambertTerm = (float) (cosAngle / distSqr);
 			lambertTerm = fmaxf(0.0f, lambertTerm);
-			if (visible<R, F>(sc, ft, shadowStart, lightPos, li, cnt)) {
+			if (visible<R, F>(sc, ft, shadowStart, lightPos, li, cnt, node)) {
 				Col c = diffuse * lightCol * lambertTerm;
 				if (s.type == FRAY_SHADER_PHONG) {
 					const V3<R> r = reflect(-toLight, n);
@@ -1205,11 +1384,11 @@ FRAY_HD Col shadeDirectBody(const DScene<R>& sc, const FlatTab& ft, const DShade
 // scene and the shared-memory tables are reached through generic pointers (LD + R2UR instead of LDS / LDC), and with 32
 // shadow rays per hit in data/boxed.fray this function is the Whitted hot loop.
 template <typename R, int F, typename RNG>
-FRAY_HD_COLD Col shadeDirect(const DScene<R> sc, const FlatTab ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, RNG& rng, RayCounters& cnt)
+FRAY_HD_COLD Col shadeDirect(const DScene<R> sc, const FlatTab ft, const DShader<R>& s, const V3<R>& rayDir, const Hit<R>& h, int node, RNG& rng, RayCounters& cnt)
 {
 	// `sc` BY VALUE: a reference would force the caller to keep the kernel's parameter block addressable, i.e. in local
 	// memory, and every table pointer of the whole kernel would then be loaded from there and dereferenced generically
-	return shadeDirectBody<R, F>(sc, ft, s, rayDir, h, rng, cnt);
+	return shadeDirectBody<R, F>(sc, ft, s, rayDir, h, node, rng, cnt);
 }
 
 // refract(), src/vector.h:184-191; returns false on total internal reflection
@@ -1244,6 +1423,7 @@ template <typename R> struct RayTask {
 	uint32_t branch;  // RNG stream of the raytrace() invocation this ray starts; GLOSSY: stream of the reflecting invocation
 	uint32_t count;   // draws already consumed from that stream; GLOSSY: draws consumed when the reflection was spawned
 	int kind;
+	int origin;       // node the ray starts on (-1: the camera), see intersectNode
 	// GLOSSY only
 	V3<R> n;          // face-forwarded normal at the hit
 	int shader, k, ns;
@@ -1269,7 +1449,7 @@ template <typename R> struct WhittedState {
 // "add weight * local shading now, push weight' * raytrace(child) for later". `spawn` numbers the children of this
 // raytrace() invocation in the order the reference would create them (RNG contract).
 template <typename R, int LEVEL, int F, typename RNG>
-FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx, const V3<R>& rayDir, int depth, const Hit<R>& h, const Col& weight,
+FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx, int node, const V3<R>& rayDir, int depth, const Hit<R>& h, const Col& weight,
                           RNG& rng, uint32_t& spawn, WhittedState<R>& ws, Col& accum, RayCounters& cnt)
 {
 	const DShader<R>& s = sc.shaders[shaderIdx];
@@ -1277,8 +1457,8 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 		case FRAY_SHADER_CONST: accum = accum + weight * loadCol(s.color); return; // src/shading.cpp:35-38
 		case FRAY_SHADER_LAMBERT:
 		case FRAY_SHADER_PHONG:
-			if (LEVEL == 0 && !Num<R>::kExact) accum = accum + weight * shadeDirectBody<R, F>(sc, ft, s, rayDir, h, rng, cnt);
-			else accum = accum + weight * shadeDirect<R, F>(sc, ft, s, rayDir, h, rng, cnt);
+			if (LEVEL == 0 && !Num<R>::kExact) accum = accum + weight * shadeDirectBody<R, F>(sc, ft, s, rayDir, h, node, rng, cnt);
+			else accum = accum + weight * shadeDirect<R, F>(sc, ft, s, rayDir, h, node, rng, cnt);
 			return;
 		case FRAY_SHADER_REFL: {
 			const V3<R> n = faceforward(rayDir, h.norm);
@@ -1287,6 +1467,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 			if (s.pureReflection) {
 				RayTask<R> t;
 				t.kind = FRAY_TASK_RAY;
+				t.origin = node;
 				t.start = start;
 				t.dir = reflect(rayDir, n);
 				t.weight = weight * loadCol(s.mult);
@@ -1299,6 +1480,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 			const int ns = depth == 0 ? s.numSamples : 3; // LOW_GLOSSY_SAMPLES, src/constants.h:36
 			RayTask<R> t;
 			t.kind = FRAY_TASK_GLOSSY;
+			t.origin = node;
 			t.start = start;
 			t.dir = rayDir;
 			t.weight = weight * loadCol(s.mult) / (float) ns;
@@ -1321,6 +1503,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 			if (!refractDir(rayDir, n, ior, refracted)) return; // total internal reflection: black
 			RayTask<R> t;
 			t.kind = FRAY_TASK_RAY;
+			t.origin = node;
 			t.start = h.ip - n * Num<R>::offsetEps(maxAbs(h.ip));
 			t.dir = refracted;
 			t.weight = weight * loadCol(s.mult);
@@ -1340,7 +1523,7 @@ FRAY_HD void shadeWhitted(const DScene<R>& sc, const FlatTab& ft, int shaderIdx,
 					const Col op = ((F & FRAY_F_TEX) && L.texture >= 0) ? sampleTexture(sc, L.texture, rayDir, h.norm, h.u, h.v) : loadCol(L.opacity);
 					w = w * (j == i ? op : (Col(1, 1, 1) - op));
 				}
-				shadeWhitted<R, (LEVEL < 2 ? LEVEL + 1 : 2), F>(sc, ft, sc.layers[s.firstLayer + i].shader, rayDir, depth, h, w, rng, spawn, ws, accum, cnt);
+				shadeWhitted<R, (LEVEL < 2 ? LEVEL + 1 : 2), F>(sc, ft, sc.layers[s.firstLayer + i].shader, node, rayDir, depth, h, w, rng, spawn, ws, accum, cnt);
 			}
 			return;
 		}
@@ -1359,7 +1542,13 @@ FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R
 	ray.dir = task.dir;
 	int node, light;
 	Hit<R> h;
-	closestHit<R, F>(sc, ft, ray, node, light, h);
+	closestHit<R, F>(sc, ft, ray, node, light, h, task.origin);
+#if defined(FRAY_DEBUG_TRACE) && !defined(__CUDA_ARCH__)
+	if (g_frayTrace)
+		printf("  ray depth %d start (%.7f %.7f %.7f) dir (%.6f %.6f %.6f) -> node %d light %d dist %.7f ip (%.6f %.6f %.6f) n (%.4f %.4f %.4f) w %.4f\n", task.depth, (double) ray.start.x,
+		       (double) ray.start.y, (double) ray.start.z, (double) ray.dir.x, (double) ray.dir.y, (double) ray.dir.z, node, light, (double) h.dist, (double) h.ip.x, (double) h.ip.y, (double) h.ip.z,
+		       node >= 0 ? (double) h.norm.x : 0.0, node >= 0 ? (double) h.norm.y : 0.0, node >= 0 ? (double) h.norm.z : 0.0, task.weight.intensity());
+#endif
 	if (light >= 0) { accum = accum + task.weight * lightEmission(sc.lights[light]); return; }
 	if (node < 0) {
 		if ((F & FRAY_F_TEX) && sc.hasEnv) accum = accum + task.weight * environmentLookup(sc, ray.dir);
@@ -1368,7 +1557,7 @@ FRAY_HD void whittedStep(const DScene<R>& sc, const FlatTab& ft, const RayTask<R
 	const DNode<R>& nd = sc.nodes[node];
 	if (F & FRAY_F_TEX) applyBump(sc, nd, h);
 	uint32_t spawn = 0;
-	shadeWhitted<R, 0, F>(sc, ft, nd.shader, ray.dir, task.depth, h, task.weight, rng, spawn, ws, accum, cnt);
+	shadeWhitted<R, 0, F>(sc, ft, nd.shader, node, ray.dir, task.depth, h, task.weight, rng, spawn, ws, accum, cnt);
 }
 
 // Takes the top entry off the ray-task stack and traces it. `primary` is the stream of the pixel sample (branch 0), which
@@ -1380,7 +1569,7 @@ FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, RNG& primary, Wh
 	if (ws.rootPending) {
 		ws.rootPending = false;
 		t.start = ws.rootStart; t.dir = ws.rootDir; t.weight = Col(1, 1, 1);
-		t.depth = 0; t.branch = 0; t.count = 0; t.kind = FRAY_TASK_RAY;
+		t.depth = 0; t.branch = 0; t.count = 0; t.kind = FRAY_TASK_RAY; t.origin = -1;
 		t.n = V3<R>(0, 0, 0); t.shader = 0; t.k = 0; t.ns = 0; t.k0 = 0;
 	} else {
 		t = ws.stack[--ws.sp];
@@ -1410,6 +1599,7 @@ FRAY_HD void whittedPop(const DScene<R>& sc, const FlatTab& ft, RNG& primary, Wh
 		}
 		RayTask<R> ray;
 		ray.kind = FRAY_TASK_RAY;
+		ray.origin = t.origin;
 		ray.start = t.start;
 		ray.dir = reflected;
 		ray.weight = t.weight;
@@ -1439,6 +1629,7 @@ template <typename R> struct PathState {
 	Col mult;   // pathMultiplier
 	int depth;
 	unsigned flags;
+	int origin; // node the segment starts on (-1: the camera), see intersectNode
 };
 
 // hemisphereSample(), src/main.cpp:92-116. cos(phi) = 2v-1 and sin(phi) = sqrt(1 - cos^2) replace acos/sin/cos.
@@ -1473,7 +1664,7 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 	ray.dir = ps.dir;
 	int node, light;
 	Hit<R> h;
-	closestHit<R, F>(sc, ft, ray, node, light, h);
+	closestHit<R, F>(sc, ft, ray, node, light, h, (F & FRAY_F_NODES) ? ps.origin : -1);
 #if defined(FRAY_DEBUG_TRACE) && !defined(__CUDA_ARCH__)
 	printf("  seg depth %d start (%.6f %.6f %.6f) dir (%.6f %.6f %.6f) -> node %d light %d dist %.6f ip (%.5f %.5f %.5f) mult %.5f draws %u\n", ps.depth, (double) ray.start.x, (double) ray.start.y,
 	       (double) ray.start.z, (double) ray.dir.x, (double) ray.dir.y, (double) ray.dir.z, node, light, (double) h.dist, (double) h.ip.x, (double) h.ip.y, (double) h.ip.z, ps.mult.intensity(), rng.count);
@@ -1552,7 +1743,7 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 						brdfZero = false;
 					}
 					// a zero BRDF makes the shadow ray pointless (the reference tests visibility first; same result)
-					if (!brdfZero && visible<R, F>(sc, ft, h.ip + h.norm * eps, onLight, li, cnt)) {
+					if (!brdfZero && visible<R, F>(sc, ft, h.ip + h.norm * eps, onLight, li, cnt, node)) {
 						const float4 em = rec[5];
 						const float probHit = 1.0f / solidAngle;
 						const float probPick = 1.0f / (float) sc.numLights;
@@ -1633,6 +1824,7 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 		pdf = 1.0f;
 	}
 	ps.depth++;
+	if (F & FRAY_F_NODES) ps.origin = node;
 	ps.mult = ps.mult * brdf / pdf;
 	return pathAlive(sc, ps);
 }
@@ -1718,6 +1910,7 @@ FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, 
 			ps.mult = Col(1, 1, 1);
 			ps.depth = 0;
 			ps.flags = 0;
+			ps.origin = -1;
 			while (pathSegment<R, F>(sc, ft, ps, rng, c, cnt)) {}
 		} else {
 			ws->setRoot(rays[e].start, rays[e].dir);

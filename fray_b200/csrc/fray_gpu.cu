@@ -251,7 +251,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	const bool randomOffsets = gi || (c->precision == FRAY_GPU_FP32 ? c->sc32.cam.dof : c->sc64.cam.dof);
 	const int spp = f->spp > 0 ? f->spp : c->defaultSpp;
 	int s0 = f->sample_begin, s1 = f->sample_end;
-	if (s0 == 0 && s1 == 0) s1 = spp;
+	if (s0 == 0 && s1 == 0 && !(f->flags & FRAY_FRAME_SAMPLE_RANGE)) s1 = spp;
 	if (s0 < 0 || s1 < s0 || s1 > spp) return fail(FRAY_GPU_EINVAL, "sample range outside [0, spp]");
 	if (!randomOffsets && spp > 5) return fail(FRAY_GPU_EINVAL, "more than 5 samples need dof or gi (fixed AA table has 5 entries, src/main.cpp:55-61)");
 	if (f->mode != FRAY_RENDER_BEAUTY && f->mode != FRAY_RENDER_AOV) return fail(FRAY_GPU_EINVAL, "unknown render mode");

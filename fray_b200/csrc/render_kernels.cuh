@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 			eyeCol = Col(0, 0, 0);
 			cnt.primary++;
 			if (GI) {
-				ps.start = first.start; ps.dir = first.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
+				ps.start = first.start; ps.dir = first.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0; ps.origin = -1;
 			} else {
 				ws.setRoot(first.start, first.dir);
 			}
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 					eyeCol = Col(0, 0, 0);
 					cnt.primary++;
 					if (GI) {
-						ps.start = rightEye.start; ps.dir = rightEye.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0;
+						ps.start = rightEye.start; ps.dir = rightEye.dir; ps.mult = Col(1, 1, 1); ps.depth = 0; ps.flags = 0; ps.origin = -1;
 					} else {
 						ws.setRoot(rightEye.start, rightEye.dir);
 					}

@@ -686,10 +686,11 @@ template <typename R> struct SceneImage {
 			}
 			// kd nodes: absolute indices + per-node boxes (in double, then rounded: the same values the reference's split() yields)
 			if (m.kd_root >= 0) {
-				struct Item { int node; double box[6]; };
+				struct Item { int node; int depth; double box[6]; };
 				std::vector<Item> todo;
 				Item root;
 				root.node = m.kd_root;
+				root.depth = 0;
 				for (int k = 0; k < 3; k++) { root.box[k] = m.bbox_min[k]; root.box[3 + k] = m.bbox_max[k]; }
 				todo.push_back(root);
 				size_t visited = 0;
@@ -697,6 +698,9 @@ template <typename R> struct SceneImage {
 					Item it = todo.back();
 					todo.pop_back();
 					if (!inRange(it.node, m.num_kd_nodes) || ++visited > (size_t) m.num_kd_nodes) { err = "malformed KD tree"; return false; }
+					// the device walks keep one pending sibling per level on a fixed stack (core.cuh, FRAY_KD_STACK); the reference's
+					// builder stops at MAX_DEPTH 64 (src/constants.h:39), a deeper tree handed in through the C ABI is refused here
+					if (it.depth >= FRAY_KD_STACK - 2) { err = "KD tree deeper than the device traversal stack (FRAY_KD_STACK - 2 levels)"; return false; }
 					const FrayGpuKdNode& n = s.kd_nodes[(size_t) m.first_kd_node + it.node];
 					DKdNode<R>& dn = kd[(size_t) m.first_kd_node + it.node];
 					for (int k = 0; k < 6; k++) kdBox[6 * ((size_t) m.first_kd_node + it.node) + k] = (R) it.box[k];
@@ -712,6 +716,7 @@ template <typename R> struct SceneImage {
 						dn.b = 0;
 						Item l = it, r = it;
 						l.node = n.a; r.node = n.a + 1;
+						l.depth = r.depth = it.depth + 1;
 						l.box[3 + n.axis] = n.split;
 						r.box[n.axis] = n.split;
 						todo.push_back(l);

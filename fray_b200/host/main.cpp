@@ -121,6 +121,7 @@ int main(int argc, char** argv)
 		else if (a == "--bucket-count") frame.bucket_count = atoi(next("--bucket-count"));
 		else if (a == "--samples") {
 			if (sscanf(next("--samples"), "%d:%d", &frame.sample_begin, &frame.sample_end) != 2) { usage(); return -1; }
+			frame.flags |= FRAY_FRAME_SAMPLE_RANGE; // literal: A == B is an empty share
 		} else if (!a.empty() && a[0] == '-') { usage(); return -1; }
 		else sceneFile = a;
 	}

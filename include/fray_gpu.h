@@ -260,6 +260,10 @@ enum {
                                  default clears them so that partial frames can be summed). For shares that write straight into
                                  ONE frame, e.g. rank 0's frame mapped into every GPU through fray_gpu_frame_import(). */
 
+#define FRAY_FRAME_SAMPLE_RANGE 4u /* [sample_begin, sample_end) is taken literally, so that begin == end is an EMPTY share
+                                 (zeros / nothing written). Without this flag 0,0 keeps meaning "all samples". Launchers that
+                                 compute ranges (r * spp / world) set it. */
+
 /* Samples per pixel by the reference's rule (src/main.cpp:395-400). */
 int fray_gpu_samples_per_pixel(const FrayGpuScene* scene);
 
@@ -267,7 +271,7 @@ typedef struct FrayGpuFrame {
 	int32_t spp;            /* total samples per pixel of the frame; 0 = fray_gpu_samples_per_pixel() */
 	uint32_t seed;          /* initRandom() seed, 42 in src/main.cpp:502 */
 	int32_t sample_begin;   /* this call renders samples [sample_begin, sample_end) of every owned pixel; */
-	int32_t sample_end;     /*   0,0 = all */
+	int32_t sample_end;     /*   0,0 = all, unless FRAY_FRAME_SAMPLE_RANGE is set */
 	int32_t bucket_rank;    /* this call owns share `bucket_rank` of `bucket_count` of the image: the frame is cut into  */
 	int32_t bucket_count;   /*   8x4 pixel tiles (row-major) and tile t belongs to share t % bucket_count -- the         */
 	                        /*   multi-GPU form of the reference's bucket list (src/sdl.cpp:243-262); 0,0 = all          */

@@ -50,3 +50,12 @@ def golden_scene(cases, name):
     import oracle_util as ou
     c = cases[name]
     return ou.override_scene(c["scene"], "golden_" + name, c["settings"], c["camera"]), c["seed"]
+
+
+def local_scene(name):
+    """tests/scenes/<name>.fray copied into the data mirror (asset paths are relative to it); the path of the copy."""
+    import shutil
+    import oracle_util as ou
+    dst = os.path.join(ou.DATA_DIR, name + "__test.fray")
+    shutil.copyfile(os.path.join(HERE, "scenes", name + ".fray"), dst)
+    return dst

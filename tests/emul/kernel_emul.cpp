@@ -14,6 +14,11 @@
 
 using namespace fray;
 
+#if defined(FRAY_DEBUG_TRACE)
+namespace fray { thread_local int g_frayTrace = 0; }
+static int tracePixel(int which) { const char* e = getenv(which ? "FRAY_TRACE_Y" : "FRAY_TRACE_X"); return e ? atoi(e) : -1; }
+#endif
+
 template <typename R, int F>
 static void renderRows(const DScene<R>& sc, const FlatTab& ft, const FrayGpuFrame& fr, int W, int H, int spp, int s0, int s1, float* out,
                        std::atomic<int>& nextRow, RayCounters& total)
@@ -43,6 +48,10 @@ static void renderRows(const DScene<R>& sc, const FlatTab& ft, const FrayGpuFram
 				continue;
 			}
 			Col sum(0, 0, 0);
+#if defined(FRAY_DEBUG_TRACE)
+			g_frayTrace = (x == tracePixel(0) && y == tracePixel(1));
+			if (g_frayTrace) printf("pixel %d %d (%s)\n", x, y, Num<R>::kExact ? "fp64" : "fp32");
+#endif
 			for (int i = s0; i < s1; i++) sum = sum + renderSample<R, F>(sc, ft, fr.seed, x, y, W, i, ws, cnt);
 			if (!(fr.flags & FRAY_FRAME_SUM)) sum = sum / (float) spp;
 			o[0] = sum.r; o[1] = sum.g; o[2] = sum.b;
@@ -65,7 +74,7 @@ static int renderT(const FrayGpuScene* scene, const FrayGpuFrame* fr, float* out
 	const int W = scene->settings.frame_width, H = scene->settings.frame_height;
 	const int spp = fr->spp > 0 ? fr->spp : samplesPerPixel(*scene);
 	int s0 = fr->sample_begin, s1 = fr->sample_end;
-	if (s0 == 0 && s1 == 0) s1 = spp;
+	if (s0 == 0 && s1 == 0 && !(fr->flags & FRAY_FRAME_SAMPLE_RANGE)) s1 = spp;
 	if (threads < 1) threads = (int) std::thread::hardware_concurrency();
 	std::atomic<int> nextRow(0);
 	RayCounters total = { 0, 0, 0 };

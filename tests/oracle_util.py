@@ -23,6 +23,7 @@ from fray_b200.scenes import DATA_DIR  # noqa: E402
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 REF_CTR = os.path.join(REF_DIR, "fray_ref_ctr")
 REF_BIN = os.path.join(REF_DIR, "fray_ref")
+REF_STRICT = os.path.join(REF_DIR, "fray_ref_strict")
 
 _oracle = None
 
@@ -121,6 +122,16 @@ def reference_render(scene_file: str, seed: int = 42, threads: int = 0, aov: boo
             node, dist = read_aov(os.path.join(td, "out.aov"))
             return rgb, sec, node, dist
         return rgb, sec
+
+
+def reference_render_unmodified(scene_file: str) -> np.ndarray:
+    """The UNMODIFIED reference (oracle/_ref/fray_ref_strict: all of src/*.cpp incl. main.cpp's RendMT::entry bucket loop and
+    libstdc++'s thread-keyed generators, strict IEEE flags) on `scene_file`; returns its framebuffer `vfb`, which the SDL
+    stand-in dumps at exit ($FRAY_DUMP). Only meaningful for scenes that draw no random numbers (parity tier T0)."""
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "vfb.f32")
+        subprocess.run([REF_STRICT, scene_file], check=True, capture_output=True, text=True, env=dict(os.environ, FRAY_DUMP=out))
+        return read_dump(out)
 
 
 def compare(a: np.ndarray, b: np.ndarray, tol: float = 1e-3):

@@ -6,6 +6,8 @@ produced by OUR parser / OBJ loader / KD builder / EXR reader, and must reproduc
 node ids and distances exactly. hw9/dragon.fray is the documented exception: its glossy floor spawns secondary rays that draw
 random numbers, where the contract derives per-ray streams (oracle/fray_rng.h), so only non-floor pixels match exactly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -65,3 +67,37 @@ def test_shards_of_the_oracle_add_up(golden_cases, data_dir):
     assert np.array_equal(sum(parts), full)  # disjoint pixels: exact
     halves = [ou.oracle_render(sc, seed=seed, flags=fb.FRAME_SUM, sample_begin=a, sample_end=b)[0] for a, b in ((0, 3), (3, 8))]
     np.testing.assert_allclose(halves[0] + halves[1], full, rtol=1e-5, atol=1e-6)
+
+
+T0 = ["forest", "forest_aa", "axe_test", "nonconvex"]
+
+
+@pytest.mark.parametrize("name", T0)
+def test_t0_unmodified_reference_loop(name, golden_cases, data_dir):
+    """Parity tier T0: tests/golden/t0_<name>.npz is the framebuffer of the UNMODIFIED reference binary --
+    RendMT::entry's own bucket and sample loop, /root/reference/src/main.cpp:323-371 -- on scenes that draw no random numbers.
+    It must equal the fray_ref_ctr golden (which pins oracle/ref_shim/ctr_driver.cpp's restatement of that loop) and our
+    restatement, bit for bit; where the binary is present the image is re-rendered live as well."""
+    t0 = np.load(os.path.join(ou.GOLDEN_DIR, "t0_" + name + ".npz"))["rgb"]
+    ref, _, _ = load_golden(name)
+    assert np.array_equal(t0, ref)
+    path, seed = golden_scene(golden_cases, name)
+    img, _ = ou.oracle_render(fb.Scene(path), seed=seed)
+    assert np.array_equal(img, t0)
+    if os.path.exists(ou.REF_STRICT):
+        assert np.array_equal(ou.reference_render_unmodified(path), t0)
+
+
+def test_oracle_converges_like_the_reference(data_dir):
+    """tests/golden/cornell_truth.npz: cornell_box 100x100 at 2048 paths/pixel rendered by the reference code under another
+    seed, plus the reference's own RMSE against it at 64 and 256 paths/pixel under the test seed. The restatement, being bit
+    exact, must reproduce those two numbers, and 256 paths must be closer to the truth than 64."""
+    z = np.load(os.path.join(ou.GOLDEN_DIR, "cornell_truth.npz"))
+    truth, seed = z["rgb"], int(z["test_seed"])
+    rmse = {}
+    for spp in (64, 256):
+        sc = fb.Scene(ou.override_scene("cornell_box", f"truth{spp}", dict(frameWidth=truth.shape[1], frameHeight=truth.shape[0], pathsPerPixel=spp)))
+        img, _ = ou.oracle_render(sc, seed=seed)
+        rmse[spp] = ou.compare(truth, img)[1]
+        assert abs(rmse[spp] - float(z[f"ref_rmse_{spp}"])) < 1e-9
+    assert rmse[256] < 0.65 * rmse[64]
