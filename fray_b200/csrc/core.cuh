@@ -224,6 +224,17 @@ FRAY_HD int floatBits(float f) // the int stored in a float4 lane
 #endif
 }
 
+FRAY_HD float intBitsToFloat(int i)
+{
+#if defined(__CUDA_ARCH__)
+	return __int_as_float(i);
+#else
+	float f;
+	memcpy(&f, &i, sizeof(f));
+	return f;
+#endif
+}
+
 template <typename R> struct DCamera {
 	R pos[3], topLeft[3], topRight[3], bottomLeft[3], front[3], up[3], right[3];
 	R w, h, aperture, focalDist, stereoSep;
@@ -284,6 +295,9 @@ template <typename R> struct DScene {
 	int flat2InfoBase;         // FlatInfo index of the first two-sided record
 	int numFlatInfo;           // all FlatInfo entries
 	unsigned shadowHex[FRAY_SHADOW_LIGHTS]; // bit k: hexahedron k can occlude a ray towards light l
+	// the light loop of Lambert / Phong as the wavefront integrator sees it (wave.cuh): samples of all lights together, and the
+	// random draws they consume (two per RectLight sample, src/lights.cpp:49-77)
+	int lightSamples, lightDraws;
 };
 
 template <typename R> struct Ray {
@@ -418,6 +432,47 @@ template <typename R> FRAY_HD bool intersectSphere(const DGeom<R>& g, const Ray<
 // Cube::intersect + intersectCubeSide, src/geometry.cpp:85-137
 template <typename R> FRAY_HD bool intersectCube(const DGeom<R>& g, const Ray<R>& ray, Hit<R>& h, bool self = false)
 {
+	if constexpr (!Num<R>::kExact) {
+		// Fast precision: the cube as three slabs -- entry = latest near plane, exit = earliest far plane; from outside the hit is
+		// the entry, from inside the exit (what the closest of the six side tests gives), for a ray that starts on this cube only
+		// the exit (its entry is its own origin). Unlike six bounded side tests, whose 1e-6 slack is below the FP32 error of a hit
+		// point at distance 20, the slab form has no cracks along the edges.
+		const V3<R> O(g.p[0], g.p[1], g.p[2]);
+		const R hs = g.p[3];
+		R tIn = -FLT_MAX, tOut = FLT_MAX;
+		int aIn = 0, aOut = 0;
+		R sIn = 0, sOut = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+		for (int axis = 0; axis < 3; axis++) {
+			const R s = ray.start.get(axis), d = ray.dir.get(axis), c = O.get(axis);
+			if (fabs(d) < (R) 1e-9) { // parallel to the slab (src/geometry.cpp:110): inside it or never
+				if (s < c - hs || s > c + hs) return false;
+				continue;
+			}
+			const R r = 1 / d;
+			const R tLo = (c - hs - s) * r, tHi = (c + hs - s) * r;
+			const R tn = fmin(tLo, tHi), tf = fmax(tLo, tHi);
+			if (tn > tIn) { tIn = tn; aIn = axis; sIn = d > 0 ? (R) -1 : (R) 1; }
+			if (tf < tOut) { tOut = tf; aOut = axis; sOut = d > 0 ? (R) 1 : (R) -1; }
+		}
+		if (!(tIn <= tOut)) return false;
+		const R tMin = self ? Num<R>::selfEps(maxAbs(O) + hs) : (R) 0;
+		const bool entry = !self && tIn >= 0;
+		if (!entry && !(tOut >= tMin)) return false;
+		const R t = entry ? tIn : tOut;
+		const int axis = entry ? aIn : aOut;
+		const R sgn = entry ? sIn : sOut;
+		h.ip = ray.start + ray.dir * t;
+		h.dist = t; // |dir| = 1
+		h.norm = V3<R>(axis == 0 ? sgn : 0, axis == 1 ? sgn : 0, axis == 2 ? sgn : 0);
+		h.u = axis == 0 ? h.ip.y : h.ip.x;
+		h.v = axis == 2 ? h.ip.y : h.ip.z;
+		h.tri = -1;
+		h.mesh = -1;
+		return true;
+	}
 	const V3<R> O(g.p[0], g.p[1], g.p[2]);
 	const R hs = g.p[3];
 	const R slack = Num<R>::slackEps(maxAbs(O) + hs);
@@ -1129,6 +1184,44 @@ template <typename R> FRAY_HD void flatBarycentrics(const DScene<R>& sc, const D
 	l3 = dot(cross(AB, H), N) * rNN;
 }
 
+// the winner `idx` of the flat-table loops (a FlatInfo index) as a hit: node or light, hit point, shading normal, (u, v)
+template <typename R, int F>
+FRAY_HD void flatResolve(const DScene<R>& sc, const FlatTab& ft, int idx, const Ray<R>& ray, int& node, int& light, Hit<R>& best)
+{
+	const FlatInfo& fi = ft.info[idx];
+	if (fi.flags & FRAY_FLAT_LIGHT) {
+		light = fi.node;
+	} else {
+		node = fi.node;
+		best.flat = idx;
+		best.ip = ray.start + ray.dir * best.dist;
+		best.norm = V3<R>(fi.nx, fi.ny, fi.nz);
+		best.u = best.v = 0;
+		best.mesh = fi.mesh;
+		best.tri = fi.tri0;
+		if ((fi.flags & FRAY_FLAT_QUAD) && fi.diag.x * best.ip.x + fi.diag.y * best.ip.y + fi.diag.z * best.ip.z + fi.diag.w < 0) best.tri = fi.tri1;
+		if ((F & FRAY_F_SPHERES) && (fi.flags & FRAY_FLAT_SPHERE)) { // info.norm = ip - O, normalised (src/geometry.cpp:71-72)
+			const float4 sp = ft.spheres[idx - sc.numFlatAll];
+			best.norm = normalized(best.ip - V3<R>(sp.x, sp.y, sp.z));
+		}
+		if ((F & FRAY_F_ATTR) && (fi.flags & FRAY_FLAT_ATTR)) {
+			const DNode<R>& nd = sc.nodes[node];
+			if (fi.flags & FRAY_FLAT_SPHERE) { // spherical coordinates of the normal, src/geometry.cpp:73-80
+				best.u = (R) ((atan2(best.norm.z, best.norm.x) / (R) FRAY_PI * 180 + 180) / 360);
+				best.v = (R) (1 - (asin(best.norm.y) / (R) FRAY_PI * 180 + 90) / 180);
+			} else if (fi.flags & FRAY_FLAT_PLANE) { // info.u = ip.x, info.v = ip.z in object space, src/geometry.cpp:45-46
+				const V3<R> q = xfUnpoint(nd.T, best.ip);
+				best.u = q.x;
+				best.v = q.z;
+			} else {
+				flatBarycentrics(sc, nd, best.tri, best.ip, best.l2, best.l3);
+				triangleAttributes(sc, fi.mesh, best.tri, best.l2, best.l3, best.norm, best.u, best.v);
+				best.norm = xfDir(nd.T, best.norm);
+			}
+		}
+	}
+}
+
 // the two closest-hit loops of raytrace()/pathtrace(), src/main.cpp:178-199, 250-271
 template <typename R, int F>
 FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>& ray, int& node, int& light, Hit<R>& best, int origin = -1)
@@ -1144,40 +1237,7 @@ FRAY_HD_HOT void closestHit(const DScene<R>& sc, const FlatTab& ft, const Ray<R>
 		if (F & FRAY_F_HEX) flatHexClosest(ft.hexes, sc.numFlatHex, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx);
 		if (F & FRAY_F_SPHERES) flatSpheresClosest(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx, sc.numFlatAll);
 		if (F & FRAY_F_TWOSIDED) flatClosest2(ft.polys2, sc.numFlat2, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, best.dist, idx, sc.flat2InfoBase);
-		if (idx >= 0) {
-			const FlatInfo& fi = ft.info[idx];
-			if (fi.flags & FRAY_FLAT_LIGHT) {
-				light = fi.node;
-			} else {
-				node = fi.node;
-				best.flat = idx;
-				best.ip = ray.start + ray.dir * best.dist;
-				best.norm = V3<R>(fi.nx, fi.ny, fi.nz);
-				best.u = best.v = 0;
-				best.mesh = fi.mesh;
-				best.tri = fi.tri0;
-				if ((fi.flags & FRAY_FLAT_QUAD) && fi.diag.x * best.ip.x + fi.diag.y * best.ip.y + fi.diag.z * best.ip.z + fi.diag.w < 0) best.tri = fi.tri1;
-				if ((F & FRAY_F_SPHERES) && (fi.flags & FRAY_FLAT_SPHERE)) { // info.norm = ip - O, normalised (src/geometry.cpp:71-72)
-					const float4 sp = ft.spheres[idx - sc.numFlatAll];
-					best.norm = normalized(best.ip - V3<R>(sp.x, sp.y, sp.z));
-				}
-				if ((F & FRAY_F_ATTR) && (fi.flags & FRAY_FLAT_ATTR)) {
-					const DNode<R>& nd = sc.nodes[node];
-					if (fi.flags & FRAY_FLAT_SPHERE) { // spherical coordinates of the normal, src/geometry.cpp:73-80
-						best.u = (R) ((atan2(best.norm.z, best.norm.x) / (R) FRAY_PI * 180 + 180) / 360);
-						best.v = (R) (1 - (asin(best.norm.y) / (R) FRAY_PI * 180 + 90) / 180);
-					} else if (fi.flags & FRAY_FLAT_PLANE) { // info.u = ip.x, info.v = ip.z in object space, src/geometry.cpp:45-46
-						const V3<R> q = xfUnpoint(nd.T, best.ip);
-						best.u = q.x;
-						best.v = q.z;
-					} else {
-						flatBarycentrics(sc, nd, best.tri, best.ip, best.l2, best.l3);
-						triangleAttributes(sc, fi.mesh, best.tri, best.l2, best.l3, best.norm, best.u, best.v);
-						best.norm = xfDir(nd.T, best.norm);
-					}
-				}
-			}
-		}
+		if (idx >= 0) flatResolve<R, F>(sc, ft, idx, ray, node, light, best);
 	}
 	if (F & FRAY_F_NODES) {
 		for (int n = 0; n < sc.numNodes; n++) {

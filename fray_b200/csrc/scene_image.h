@@ -784,6 +784,12 @@ template <typename R> struct SceneImage {
 			o.areaF = (float) l.area;
 			if (l.type == FRAY_LIGHT_RECT && (l.x_subd < 1 || l.y_subd < 1)) { err = "RectLight subdivisions must be >= 1"; return false; }
 		}
+		d.lightSamples = d.lightDraws = 0;
+		for (int i = 0; i < s.num_lights; i++) {
+			const int ns = s.lights[i].type == FRAY_LIGHT_RECT ? s.lights[i].x_subd * s.lights[i].y_subd : 1;
+			d.lightSamples += ns;
+			if (s.lights[i].type == FRAY_LIGHT_RECT) d.lightDraws += 2 * ns;
+		}
 		// compact sampling records of the lights for the fast path tracer (core.cuh, LightRec)
 		std::vector<float4> lightRecs((size_t) FRAY_LIGHT_REC_VEC * s.num_lights);
 		for (int i = 0; i < s.num_lights; i++) {
