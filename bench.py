@@ -2,13 +2,17 @@
 """bench.py -- the headline benchmark: Mrays/s and ms/frame on data/cornell_box.fray (400x400, Monte-Carlo path tracing at
 256 paths per pixel, BASELINE.json configs[2]) on N B200s of one node, next to fray's own CPU renderer.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one frame. `value` is whole-job throughput with the scene resident in HBM: rays of the frame (closest-hit +
-any-hit queries, counted on the device) over the device time of render kernel + NCCL reduce + resolve, max over ranks.
-`e2e` is the same frame through the public call with host buffers (fray_gpu_render: kernel parameters up, framebuffer
+any-hit queries, counted on the device) over the device time of the render kernels + the multi-GPU exchange + resolve, max over
+ranks. `e2e` is the same frame through the public call with host buffers (fray_gpu_render: kernel parameters up, framebuffer
 down into pinned host memory). One JSON line on stdout (rank 0).
+
+--config selects another BASELINE.json configuration (c1 boxed, c2 zaphod, c3 cornell_box = the default and the headline,
+c4 smallpt at 1024 paths/pixel, c5 forest at 3840x2160); the default run also times the other four briefly on rank 0 at N=1
+and reports them under `other_configs`, so that one driver run records all five.
 """
 from __future__ import annotations
 
@@ -25,16 +29,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-SCENE = "cornell_box"
-SPP = 256
-METRIC = "Mrays/s (cornell_box.fray 400x400, GI 256 paths/pixel)"
 UNIT = "Mrays/s"
-# algorithmic work per ray of this workload under the cost model of SURVEY.md section 8(d), derived with the instrumented
-# oracle (tools/work_profile.py, DESIGN.md "Measurement"): 6.97 node tests, 6.97 root-box tests, 12.8 cull tests,
-# 6.45 triangle tests, 0.54 light tests, 0.46 light samples, 0.86 hemisphere samples, 0.36 BRDF evals per ray
-FLOP_PER_RAY = 937.0
-BYTES_PER_RAY = 1430.0
-NCU_DRAM_BYTES_PER_LAUNCH = 191744 + 12758272
+# flop_per_ray: ALGORITHMIC work per ray of the workload under the cost model of SURVEY.md section 8(d) -- what the reference's
+# algorithm does per ray (per-node transforms and box tests included), counted with the instrumented oracle
+# (tests/oracle_util.py: algorithmic_work_per_ray; DESIGN.md "Measurement"). It is NOT the number of instructions these kernels
+# execute: the flat tables remove most of that work, so `roofline.frac` reads "reference work per second against the FP32
+# peak", and the executed-FP32 share of the pipe is reported next to it from the ncu capture of the same build (`roofline.ncu`).
+CONFIGS = {
+    "c1": dict(scene="boxed", settings=None, flop_per_ray=1000.0, integrator="Whitted, 1 sample/pixel, two 4x4 rectangular lights",
+               baseline="configs[0]", kernel="waveTraceKernel / waveShadeKernel / waveShadowKernel (wavefront Whitted)"),
+    "c2": dict(scene="zaphod", settings=None, flop_per_ray=270.0, integrator="Whitted, depth of field 100 samples/pixel",
+               baseline="configs[1]", kernel="renderKernel<float, Whitted, flat table + textures + lens>"),
+    "c3": dict(scene="cornell_box", settings=dict(pathsPerPixel=256), flop_per_ray=937.0, bytes_per_ray=1430.0, integrator="GI 256 paths/pixel",
+               baseline="configs[2]", kernel="renderKernel<float, GI, FRAY_F_FLAT|FRAY_F_HEX>"),
+    "c4": dict(scene="smallpt", settings=dict(pathsPerPixel=1024), flop_per_ray=650.0, integrator="GI 1024 paths/pixel",
+               baseline="configs[3]", kernel="renderKernel<float, GI, flat table + spheres + two-sided list>",
+               cpu_settings=dict(pathsPerPixel=64)),  # the in-run CPU leg renders 64 of the 1024 paths per pixel (~10 s instead of ~3 min)
+    "c5": dict(scene="forest", settings=dict(interactive="off", frameWidth=3840, frameHeight=2160), flop_per_ray=1100.0, integrator="Whitted, 1 sample/pixel",
+               baseline="configs[4]", kernel="waveTraceKernel / waveShadeKernel / waveShadowKernel (wavefront Whitted)",
+               reference_settings=dict(interactive="off", frameWidth=1920, frameHeight=1080),
+               reference_note="the reference's framebuffer stops at 3000 pixels a side (VFB_MAX_SIZE, src/constants.h:27): its arm renders 1920x1080"),
+}
+HEADLINE = "c3"
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x FP32 lanes x 2 (FMA) x max SM clock
 
 
@@ -107,84 +123,128 @@ class ClockSampler:
                 "samples": len(rows), "reasons": sorted(reasons)}
 
 
-def bench_scene_file(spp: int, extra: dict | None = None) -> str:
+def scene_file(cfg: dict, extra: dict | None = None, settings_key: str = "settings") -> str:
     from fray_b200.scenes import override_scene
-    st = dict(pathsPerPixel=spp)
+    st = dict(cfg.get(settings_key) or cfg.get("settings") or {})
     st.update(extra or {})
-    tag = "bench_" + "_".join(f"{k}{v}" for k, v in sorted(st.items()))
-    return override_scene(SCENE, tag, st)
+    tag = "bench_" + ("_".join(f"{k}{v}" for k, v in sorted(st.items())) or "default")
+    return override_scene(cfg["scene"], tag, st or None)
+
+
+def workload_name(cfg: dict, W: int, H: int) -> str:
+    return f"{cfg['scene']}.fray {W}x{H}, {cfg['integrator']} (BASELINE.json {cfg['baseline']})"
+
+
+def metric_name(cfg: dict, W: int, H: int) -> str:
+    return f"Mrays/s ({cfg['scene']}.fray {W}x{H}, {cfg['integrator']})"
+
+
+def reference_frame_seconds(ou, scene_path: str, kind: str, sc, cores: int) -> float:
+    if kind == "reference":
+        out = subprocess.run([ou.REF_BIN, scene_path], capture_output=True, text=True, check=True).stdout
+        return float(re.search(r"Render took ([0-9.]+)s", out).group(1))
+    t = time.time()
+    ou.oracle_render(sc, threads=cores)
+    return time.time() - t
 
 
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's own multithreaded CPU renderer (oracle/_ref/fray_ref, unmodified sources built
-    headless) on this host's cores. Each step renders a bounded sample of the workload: the same scene at 40 paths/pixel
-    (the scene file's default) instead of 256; rays are counted by the oracle on the identical configuration."""
+    headless) on this host's cores, on the SAME configuration as our arm: each step renders the whole frame. If the whole run
+    would not end within ~5 minutes the remaining steps fall back to a bounded sample of the workload (fewer paths per pixel;
+    the metric is a rate) and the line says so. Rays are counted by the oracle on the identical configuration."""
     if rank != 0:
         return
     import fray_b200 as fb
     import oracle_util as ou
+    cfg = CONFIGS[args.config]
     cores = min(64, os.cpu_count() or 1)  # the reference's pool holds at most 64 threads (src/cxxptl-sdl.h:48)
-    sample_spp = 40
-    f = bench_scene_file(sample_spp, dict(numThreads=cores, wantPrepass="off"))
     kind = "reference" if os.path.exists(ou.REF_BIN) else "port"
+    extra = dict(numThreads=cores, wantPrepass="off")
+    f = scene_file(cfg, extra, "reference_settings")
     sc = fb.Scene(f)
-    # rays of the sample frame (the ray count is a property of (scene, seed), see tests: GPU fp64 == oracle one for one)
-    _, ostats = ou.oracle_render(sc)
+    _, ostats = ou.oracle_render(sc, threads=cores)  # the ray count is a property of (scene, seed): GPU fp64 == oracle one for one (tests)
     rays = ostats.rays
-
-    def one_frame() -> float:
-        if kind == "reference":
-            out = subprocess.run([ou.REF_BIN, f], capture_output=True, text=True, check=True).stdout
-            return float(re.search(r"Render took ([0-9.]+)s", out).group(1))
-        t = time.time()
-        ou.oracle_render(sc, threads=cores)
-        return time.time() - t
-
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        one_frame()
-    times = [one_frame() for _ in range(args.steps)]
+    sample = f"the whole frame: {cfg['scene']}.fray {sc.width}x{sc.height} at {sc.spp} samples/pixel ({rays} rays)"
+    same = "reference_settings" not in cfg
+    first = reference_frame_seconds(ou, f, kind, sc, cores)  # warm-up frame (also sizes the run)
+    if first * (args.steps + 1) > 300.0 and cfg["settings"] and "pathsPerPixel" in cfg["settings"]:
+        spp = max(8, int(cfg["settings"]["pathsPerPixel"] * 240.0 / (first * (args.steps + 1))))
+        f = scene_file(cfg, dict(extra, pathsPerPixel=spp))
+        sc = fb.Scene(f)
+        _, ostats = ou.oracle_render(sc, threads=cores)
+        rays = ostats.rays
+        sample = f"bounded sample: {cfg['scene']}.fray {sc.width}x{sc.height} at {spp} of {cfg['settings']['pathsPerPixel']} paths/pixel ({rays} rays) per step"
+        same = False
+    times = [reference_frame_seconds(ou, f, kind, sc, cores) for _ in range(args.steps)]
     sec = sum(times) / len(times)
     value = rays / sec / 1e6
+    W, H = (sc.width, sc.height)
+    full = fb.Scene(scene_file(cfg))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cornell_box.fray 400x400 GI, bounded sample: 40 paths/pixel per step (full workload 256)", "host_threads": cores},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"cornell_box.fray 400x400 at 40 paths/pixel ({rays} rays), {kind} renderer, mean of {args.steps} frames"},
+        "impl": "reference", "metric": metric_name(cfg, full.width, full.height), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, full.width, full.height), "host_threads": cores, "step": sample, "same_config": same,
+                   "note": cfg.get("reference_note", "one warm-up frame, then every step renders the frame again")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + f", {kind} renderer, mean of {args.steps} frames"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def cpu_baseline(log_fn) -> dict:
-    """The reference's own CPU renderer on the same frame (rank 0, N=1 only): ~25 s of CPU work (one pass of the oracle port for
-    the ray count and the work profile, two of the reference binary)."""
+def cpu_baseline(cfg: dict, gpu_frame, log_fn) -> tuple[dict, dict]:
+    """The reference's own CPU renderer on the same frame (rank 0, N=1 only): one pass of the oracle port (ray count, work
+    profile and the image our frame is compared with), then the reference binary, best of two frames. ~25 s for the headline."""
+    import numpy as np
+
     import fray_b200 as fb
     import oracle_util as ou
     cores = min(64, os.cpu_count() or 1)
-    sample_spp = SPP  # the whole 256-path frame: ~8 s per frame on 16 threads, ~25 s for this leg
-    f = bench_scene_file(sample_spp, dict(numThreads=cores, wantPrepass="off"))
+    f = scene_file(cfg, dict(numThreads=cores, wantPrepass="off"), "cpu_settings" if "cpu_settings" in cfg else "reference_settings")
     sc = fb.Scene(f)
     t = time.time()
-    _, ostats = ou.oracle_render(sc, threads=cores)
+    want, ostats = ou.oracle_render(sc, threads=cores, seed=42)
     port_sec = time.time() - t
     prof = ou.oracle_work_profile()
     flop, byts = ou.algorithmic_work_per_ray(prof, ostats.rays)
     if os.path.exists(ou.REF_BIN):
         best = None
         for _ in range(2):
-            out = subprocess.run([ou.REF_BIN, f], capture_output=True, text=True, check=True).stdout
-            sec = float(re.search(r"Render took ([0-9.]+)s", out).group(1))
+            sec = reference_frame_seconds(ou, f, "reference", sc, cores)
             best = sec if best is None else min(best, sec)
         kind, sec = "reference", best
     else:
         kind, sec = "port", port_sec
     log_fn(f"cpu baseline ({kind}, {cores} threads): {sec:.2f} s for {ostats.rays} rays; oracle port {port_sec:.2f} s; "
            f"algorithmic work {flop:.0f} flop/ray {byts:.0f} B/ray")
-    return {"value": ostats.rays / sec / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"cornell_box.fray 400x400 at {sample_spp} paths/pixel, the full frame ({ostats.rays} rays by the reference's count), best of 2 frames",
+    base = {"value": ostats.rays / sec / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{cfg['scene']}.fray {sc.width}x{sc.height} at {sc.spp} samples/pixel, the full frame ({ostats.rays} rays by the reference's count), best of 2 frames",
             "ms_per_frame_sample": sec * 1e3, "flop_per_ray_measured": flop, "bytes_per_ray_measured": byts}
+    parity = None
+    if gpu_frame is not None and gpu_frame.shape == want.shape and "cpu_settings" not in cfg:
+        frac, rmse, mx = ou.compare(want, gpu_frame, 1e-3)
+        parity = {"against": "oracle/ FP64 restatement of the reference (bit-exact with fray_ref_ctr on the goldens), same seed 42, same frame",
+                  "rmse": rmse, "frac_within_1e-3": frac, "max_abs_diff": mx,
+                  "mean_gpu": float(np.mean(gpu_frame)), "mean_oracle": float(np.mean(want))}
+    return base, parity
+
+
+def quick_config(fb, name: str, device: int, peak: float) -> dict:
+    """One BASELINE configuration timed briefly on one GPU (device-resident, best of 5 frames after 2 warm-up frames)."""
+    cfg = CONFIGS[name]
+    sc = fb.Scene(scene_file(cfg))
+    ctx = fb.GpuContext(sc, device, fb.FP32)
+    best = None
+    for it in range(7):
+        _, st = ctx.render(seed=42)
+        if it >= 2 and (best is None or st.device_ms < best.device_ms):
+            best = st
+    ctx.close()
+    tf = best.rays * cfg["flop_per_ray"] / (best.device_ms * 1e-3) / 1e12
+    return {"config": name, "workload": workload_name(cfg, sc.width, sc.height), "ms_per_frame": best.device_ms, "rays_per_frame": best.rays,
+            "mrays_s": best.rays / best.device_ms / 1e3, "kernel_launches": best.kernel_launches, "algorithmic_flop_per_ray": cfg["flop_per_ray"],
+            "roofline_frac_algorithmic": tf / peak, "kernel": cfg["kernel"], "timing": "kernel time (CUDA events), best of 5 frames, one GPU"}
 
 
 def main():
@@ -193,11 +253,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=SPP, help="paths per pixel (the headline config is 256)")
+    ap.add_argument("--config", default=HEADLINE, choices=sorted(CONFIGS), help="BASELINE.json configuration (c3 = cornell_box 256 paths/pixel, the headline)")
+    ap.add_argument("--spp", type=int, default=0, help="override the paths per pixel of a path-traced configuration")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--split", default="auto", choices=["tiles", "p2p", "samples", "auto"],
                     help="multi-GPU decomposition: tiles (BASELINE.json for cornell; NCCL reduce), p2p (tiles written straight into rank 0's frame), samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     capture_stdout()
 
@@ -226,8 +288,12 @@ def main():
         torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
+    cfg = dict(CONFIGS[args.config])
+    if args.spp:
+        cfg["settings"] = dict(cfg.get("settings") or {}, pathsPerPixel=args.spp)
+        cfg["integrator"] = re.sub(r"\d+ paths/pixel", f"{args.spp} paths/pixel", cfg["integrator"])
     precision = fb.FP32 if args.precision == "fp32" else fb.FP64
-    scene = fb.Scene(bench_scene_file(args.spp))
+    scene = fb.Scene(scene_file(cfg))
     W, H, spp = scene.width, scene.height, scene.spp
     r = fdist.DistributedRenderer(scene, mode=args.split, precision=precision, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -241,6 +307,7 @@ def main():
     # ---- device-resident throughput ----
     for _ in range(max(args.warmup, 3)):
         r.render_device()
+        r.stats()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -264,7 +331,7 @@ def main():
         st = r.stats()  # syncs; per-step kernel time + ray counters of this rank
         kernel_ms.append(st.device_ms)
         rays_step = st.rays
-        launches_step = st.kernel_launches + (1 if (rank == 0 and r.mode != "p2p") else 0)  # render (+ combine), and resolve on rank 0
+        launches_step = st.kernel_launches + (1 if (rank == 0 and r.mode != "p2p") else 0)  # this rank's render kernels, and resolve on rank 0
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -287,14 +354,17 @@ def main():
     host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     host_np = host.numpy()
     cam = scene.head.camera
+    frame_np = None
 
     def e2e_step():
+        nonlocal frame_np
         if world == 1:
             r.ctx.update_camera(cam)          # this frame's input (kernel parameters travel host -> device with the launch)
             r.ctx.render(out=host_np, spp=spp)  # kernels + device -> pinned host copy of the frame
+            frame_np = host_np
         else:
             r.ctx.update_camera(cam)
-            r.render()
+            frame_np = r.render()
     for _ in range(2):
         e2e_step()
     barrier()
@@ -309,38 +379,59 @@ def main():
     e2e_ms = float(e2e_t[0])
     e2e_value = rays_frame / (e2e_ms * 1e-3) / 1e6
 
+    # ---- multi-GPU: rank 0's assembled frame against the same frame rendered by ONE GPU ----
+    multi_check = None
+    if world > 1 and rank == 0:
+        single, _ = r.ctx.render(seed=42, spp=spp)
+        d = np.abs(single.astype(np.float64) - frame_np.astype(np.float64))
+        multi_check = {"against": "the same frame rendered by rank 0's GPU alone (same seed)", "max_abs_diff": float(d.max()),
+                       "bit_identical": bool(np.array_equal(single, frame_np)), "frac_within_1e-5": float((d.max(axis=-1) <= 1e-5).mean()),
+                       "note": "tile splits are bit-identical; a sample split regroups the FP32 partial sums of a pixel"}
+
     if rank == 0:
         fp32_peak, l2_peak = fb.measure_peaks(local_rank, 20.0)
         kernel_ms_per_launch = kernel_total_ms / args.steps
-        achieved_tflops = rays_step * FLOP_PER_RAY / (kernel_ms_per_launch * 1e-3) / 1e12
+        flop_per_ray = cfg["flop_per_ray"]
+        achieved_tflops = rays_step * flop_per_ray / (kernel_ms_per_launch * 1e-3) / 1e12
         roofline = {
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the ncu --set full
-            # capture profiles/r01_v34_cornell256_ncu_summary.txt (0.19 MB read + 12.8 MB written: the part of the 61 MB chunk-sum scratch
-            # that left the L2 during the cold, serialised ncu pass; the scene tables never leave the SMs)
-            "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.spp == SPP and world == 1 and precision == fb.FP32) else None,
+            "frac_is": "ALGORITHMIC: rays/s x the reference algorithm's flop per ray (SURVEY.md 8d cost model), i.e. reference work per second "
+                       "against the FP32 peak -- not the share of the pipe these kernels keep busy (see `ncu` for that)",
+            # no DRAM figure is pasted here: the scene (< 1 MB) and the frame live in L2, see profiles/ for the ncu capture of this build
+            "traffic": None,
             "peak_source": "FFMA micro-benchmark run in this process (fray_gpu_measure_peaks); MEASURED_PEAKS.json holds no FP32 figure",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
-            "kernel": "renderKernel<float, GI, FRAY_F_FLAT|FRAY_F_HEX>" if precision == fb.FP32 else "renderKernel<double, GI, FRAY_F_GENERIC>",
-            "kernel_ms_per_launch": kernel_ms_per_launch, "algorithmic_flop_per_ray": FLOP_PER_RAY, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
-            "table_reads": {"algorithmic_gbs": rays_step * BYTES_PER_RAY / (kernel_ms_per_launch * 1e-3) / 1e9, "l2_peak_gbs": l2_peak,
-                            "note": "the reference's per-ray table reads (node, box, triangle records); this kernel stages them once per CTA in shared "
-                                    "memory, so they are served by LDS.128 broadcasts, not by L2 (lts throughput < 2 % in the ncu capture)"},
-            "hbm_note": "scene (<1 MB) and framebuffer (1.9 MB) are L1/L2 resident; HBM traffic is negligible",
+            "kernel": cfg["kernel"] if precision == fb.FP32 else "renderKernel<double, ...> (parity precision)",
+            "kernel_ms_per_launch": kernel_ms_per_launch, "algorithmic_flop_per_ray": flop_per_ray,
         }
+        if "bytes_per_ray" in cfg:
+            roofline["algorithmic_bytes_per_ray"] = cfg["bytes_per_ray"]
+            roofline["table_reads"] = {"algorithmic_gbs": rays_step * cfg["bytes_per_ray"] / (kernel_ms_per_launch * 1e-3) / 1e9, "l2_peak_gbs": l2_peak,
+                                       "note": "the reference's per-ray table reads (node, box, triangle records); this kernel stages them once per CTA in "
+                                               "shared memory, so they are served by LDS.128 broadcasts, not by L2"}
+        ncu_file = os.path.join(ROOT, "profiles", f"ncu_{args.config}.json")  # written by tools/ncu_summary.py --json from the capture of this build
+        if os.path.exists(ncu_file) and precision == fb.FP32:
+            with open(ncu_file) as fp:
+                roofline["ncu"] = json.load(fp)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": metric_name(cfg, W, H), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if precision == fb.FP32 else "f64", "data": "synthetic",
-            "config": {"workload": f"cornell_box.fray {W}x{H}, GI {spp} paths/pixel (BASELINE.json configs[2])", "rays_per_frame": int(rays_frame),
+            "config": {"workload": workload_name(cfg, W, H), "rays_per_frame": int(rays_frame),
                        "split": r.mode if world > 1 else "none", "l2": "flushed between timed frames (256 MB write)", "seed": 42},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * 12},
-            "gpu_launches": args.steps * launches_step,  # renderKernel + combineKernel + resolveKernel per frame (rank 0)
+            "gpu_launches": args.steps * launches_step,
             "roofline": roofline,
         }
+        if multi_check:
+            line["multi_gpu_check"] = multi_check
+        if world == 1 and not args.no_other_configs and args.config == HEADLINE and precision == fb.FP32:
+            line["other_configs"] = [quick_config(fb, name, local_rank, fp32_peak) for name in sorted(CONFIGS) if name != HEADLINE]
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(log)
+            line["cpu_baseline"], parity = cpu_baseline(cfg, np.array(frame_np) if (args.config != "c5") else None, log)
+            if parity:
+                line["parity"] = parity
         emit(line)
     if world > 1:
         dist.barrier()

@@ -1,7 +1,7 @@
 """Build recipes for the native parts of fray_b200 (explicit compiler invocations, everything in-tree).
 
   libfray_host.so   g++   fray_b200/host/*.cpp                       the CPU-side scene layer
-  libfray_gpu.so    nvcc  fray_b200/csrc/{fray_gpu,render_fp32,render_fp64}.cu   sm_100a only
+  libfray_gpu.so    nvcc  fray_b200/csrc/{fray_gpu,render_fp32,render_wave,render_fp64}.cu   sm_100a only
   fray              g++   fray_b200/host/main.cpp                    the `fray [--gpu] scene.fray` command line tool
 nvcc cross-compiles without a GPU, so this runs in the build container and the .so files travel to the GPU box.
 """
@@ -68,8 +68,9 @@ def build_cli(force: bool = False) -> str:
 def build_gpu(force: bool = False, verbose_ptxas: bool = False) -> str:
     out = os.path.join(HERE, "libfray_gpu.so")
     os.makedirs(BUILD, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("core.cuh", "flat.cuh", "rng.cuh", "render_kernels.cuh", "scene_image.h")] + [os.path.join(INCLUDE, "fray_gpu.h")]
-    units = [("fray_gpu.cu", []), ("render_fp32.cu", ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]), ("render_fp64.cu", ["-fmad=false"])]
+    headers = [os.path.join(CSRC, h) for h in ("core.cuh", "flat.cuh", "rng.cuh", "render_kernels.cuh", "scene_image.h", "wave.cuh", "wave_kernels.cuh")] + [os.path.join(INCLUDE, "fray_gpu.h")]
+    fast = ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
+    units = [("fray_gpu.cu", []), ("render_fp32.cu", fast), ("render_wave.cu", fast), ("render_fp64.cu", ["-fmad=false"])]
     extra = ["-Xptxas", "-v"] if verbose_ptxas else []
     jobs = []
     for src, flags in units:

@@ -278,6 +278,9 @@ template <typename R> struct DScene {
 	// fast precision only: FRAY_LIGHT_REC_VEC float4 per light, what explicitLightSample needs in six 128-bit loads:
 	// {type, xSubd, ySubd, samples} {centre, area} {sample-grid corner, 1 / xSubd} {column step} {row step} {colour * power}
 	const float4* lightRecs;
+	// fast precision only: world-space bounding box of every node's geometry, two vectors per node {min, -} {max, -}, padded by
+	// more than the object-space box slack: a ray that misses it cannot hit the node (wave.cuh skips the node's ray transform)
+	const float4* nodeBox;
 	// fast precision only (flat.cuh): world-space convex polygons of the brute-force meshes and the rectangular lights
 	const float4* flatPolys;   // FRAY_FLAT_POLY_VEC float4 per polygon
 	const FlatInfo* flatInfo;  // one per polygon
@@ -804,6 +807,22 @@ FRAY_HD bool intersectLeafGeom(const DScene<R>& sc, int gi, const Ray<R>& ray, R
 			else ok = intersectMeshFast<ANYHIT>(sc, g.mesh, ray, maxT, h);
 			if (ok && needAttr) triangleAttributes(sc, g.mesh, h.tri, h.l2, h.l3, h.norm, h.u, h.v);
 			break;
+		default: ok = false; break;
+	}
+	if (ok) h.geom = gi;
+	return ok;
+}
+
+// the analytic primitives only (wave.cuh: meshes go through kdWalk there, and this keeps the mesh walk out of its kernels)
+template <typename R>
+FRAY_HD bool intersectAnalytic(const DScene<R>& sc, int gi, const Ray<R>& ray, Hit<R>& h, bool needUV, bool self)
+{
+	const DGeom<R>& g = sc.geoms[gi];
+	bool ok;
+	switch (g.type) {
+		case FRAY_GEOM_PLANE: ok = intersectPlane(g, ray, h); break;
+		case FRAY_GEOM_SPHERE: ok = intersectSphere(g, ray, h, needUV, self); break;
+		case FRAY_GEOM_CUBE: ok = intersectCube(g, ray, h, self); break;
 		default: ok = false; break;
 	}
 	if (ok) h.geom = gi;

@@ -10,10 +10,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
 #include "render_kernels.cuh"
+#include "wave_kernels.cuh"
 #include "scene_image.h"
 
 using namespace fray;
@@ -55,6 +57,19 @@ struct FrayGpuCtx {
 	float* dFrame = nullptr;     // own framebuffer for fray_gpu_render
 	float* hStaging = nullptr;   // pinned
 	int occGI = -1, occWhitted = -1;
+	// wavefront Whitted path (wave_kernels.cuh): queues, accumulators, counters; grown on demand
+	void* dWave = nullptr;          // one allocation, carved up by waveLayout()
+	size_t waveBytes = 0;
+	unsigned waveRayCap = 0, waveLitCap = 0, waveHitCap = 0;
+	unsigned* dWaveCtr = nullptr;
+	WaveLaunch waveCfg = { 0, 0, nullptr, 0, 0, 0 };
+	bool waveLast = false;          // the last render went through the wavefront path
+	FrayGpuFrame lastFrame = {};
+	float* lastOut = nullptr;
+	bool lastTimed = false;
+	int waveFan = 1;                // secondary rays one hit can spawn (glossy samples), for the first guess of the queue size
+	bool waveSecondary = false;     // some node's shader reflects or refracts: the ray tree is deeper than the camera rays
+	int waveLitPerRay = 1;          // Lambert / Phong evaluations one hit can ask for (through Layered shaders)
 	bool pendingStats = false;
 	int launches = 0;
 	cudaStream_t lastStream = nullptr;
@@ -154,6 +169,8 @@ void fray_gpu_destroy(FrayGpuCtx* c)
 	cudaFree(c->dError);
 	cudaFree(c->dFrame);
 	cudaFree(c->dShared);
+	cudaFree(c->dWave);
+	cudaFree(c->dWaveCtr);
 	if (c->hStaging) cudaFreeHost(c->hStaging);
 	if (c->evStart) cudaEventDestroy(c->evStart);
 	if (c->evStop) cudaEventDestroy(c->evStop);
@@ -188,6 +205,34 @@ int fray_gpu_create(const FrayGpuScene* scene, int device, int precision, FrayGp
 		return fail(FRAY_GPU_EINVAL, err);
 	}
 	c->features = precision == FRAY_GPU_FP32 ? c->img32.features : c->img64.features;
+	for (int i = 0; i < scene->num_shaders; i++)
+		if (scene->shaders[i].type == FRAY_SHADER_REFL && !scene->shaders[i].pure_reflection) c->waveFan = std::max(c->waveFan, scene->shaders[i].num_samples);
+	{
+		// lit evaluations per hit: Lambert / Phong leaves of a node's shader tree
+		std::function<int(int, int)> litLeaves = [&](int si, int depth) -> int {
+			if (si < 0 || si >= scene->num_shaders || depth > 4) return 0;
+			const FrayGpuShader& sh = scene->shaders[si];
+			if (sh.type == FRAY_SHADER_LAMBERT || sh.type == FRAY_SHADER_PHONG) return 1;
+			int n = 0;
+			if (sh.type == FRAY_SHADER_LAYERED)
+				for (int k = 0; k < sh.num_layers && sh.first_layer + k < scene->num_layers; k++) n += litLeaves(scene->layers[sh.first_layer + k].shader, depth + 1);
+			return n;
+		};
+		for (int i = 0; i < scene->num_nodes; i++) c->waveLitPerRay = std::max(c->waveLitPerRay, litLeaves(scene->nodes[i].shader, 0));
+		std::vector<int> todo;
+		std::vector<char> seen(scene->num_shaders, 0);
+		for (int i = 0; i < scene->num_nodes; i++) todo.push_back(scene->nodes[i].shader);
+		while (!todo.empty()) {
+			const int si = todo.back();
+			todo.pop_back();
+			if (si < 0 || si >= scene->num_shaders || seen[si]) continue;
+			seen[si] = 1;
+			const FrayGpuShader& sh = scene->shaders[si];
+			if (sh.type == FRAY_SHADER_REFL || sh.type == FRAY_SHADER_REFR) c->waveSecondary = true;
+			if (sh.type == FRAY_SHADER_LAYERED)
+				for (int k = 0; k < sh.num_layers && sh.first_layer + k < scene->num_layers; k++) todo.push_back(scene->layers[sh.first_layer + k].shader);
+		}
+	}
 	const std::vector<unsigned char>& blob = precision == FRAY_GPU_FP32 ? c->img32.blob : c->img64.blob;
 
 #define CREATE_TRY(expr)                                                                   \
@@ -241,6 +286,124 @@ static int pow2Floor(int v)
 	int p = 1;
 	while (p * 2 <= v) p *= 2;
 	return p;
+}
+
+// ---- wavefront Whitted path ------------------------------------------------------------------------------------------------
+// Fast precision, Whitted integrator, a generic node loop (KD meshes / analytic primitives) and no CSG: wave_kernels.cuh.
+// FRAY_GPU_NO_WAVE=1 keeps such scenes on the megakernel (A/B timing).
+static bool waveEligible(const FrayGpuCtx* c, const FrayGpuFrame* f)
+{
+	if (c->precision != FRAY_GPU_FP32 || c->sc32.gi || f->mode != FRAY_RENDER_BEAUTY) return false;
+	if (!WaveVariants::covers(c->features)) return false;
+	if (c->sc32.maxTraceDepth + 3 > FRAY_WAVE_MAX || c->sc32.numNodes > 65000) return false;
+	static const bool off = getenv("FRAY_GPU_NO_WAVE") != nullptr;
+	return !off;
+}
+
+static int waveAllocate(FrayGpuCtx* c, unsigned numPrimary)
+{
+	// first guess: every primary hit spawns `fan` secondary rays (glossy samples), capped; SHADE raises a flag when a queue is
+	// full, waveFinish() then doubles the queues and renders the frame again
+	if (c->waveRayCap == 0) {
+		double guess = c->waveSecondary ? (double) numPrimary * std::min(std::max(c->waveFan, 1), 8) + (1 << 20) : (double) (64 * 1024);
+		if (c->sc32.cam.stereoSep > 0) guess += (double) numPrimary; // the right eyes travel through the queue of wave 1
+		c->waveRayCap = (unsigned) std::min(guess, 6.0e8);
+	}
+	c->waveRayCap = (c->waveRayCap + FRAY_WAVE_REGIONS - 1) / FRAY_WAVE_REGIONS * FRAY_WAVE_REGIONS; // FRAY_WAVE_REGIONS equal sub-queues
+	const unsigned hitCap = std::max(numPrimary, c->waveRayCap);
+	if ((double) hitCap * c->waveLitPerRay >= 4.0e9) return fail(FRAY_GPU_ENOMEM, "the lit records of this frame do not fit the wavefront queues");
+	const unsigned litCap = hitCap * (unsigned) c->waveLitPerRay; // a fixed place for every record: ray i, evaluation k -> slot i * litPerRay + k
+	const size_t pixels = (size_t) c->width * c->height;
+	const size_t need = (size_t) c->waveRayCap * 2 * (3 * sizeof(float4) + sizeof(uint2)) + (size_t) hitCap * (sizeof(float4) + sizeof(int2)) +
+	                    (size_t) litCap * (5 * sizeof(float4) + sizeof(uint2)) + pixels * 3 * sizeof(long long) + 4096;
+	if (need > c->waveBytes || hitCap > c->waveHitCap || litCap > c->waveLitCap) {
+		cudaFree(c->dWave);
+		c->dWave = nullptr;
+		c->waveBytes = 0;
+		CUDA_TRY(cudaMalloc(&c->dWave, need));
+		c->waveBytes = need;
+		c->waveHitCap = hitCap;
+		c->waveLitCap = litCap;
+	}
+	if (!c->dWaveCtr) CUDA_TRY(cudaMalloc(&c->dWaveCtr, FRAY_WCTR_COUNT * sizeof(unsigned)));
+	return FRAY_GPU_OK;
+}
+
+static void waveLayout(const FrayGpuCtx* c, WaveParams& w)
+{
+	char* b = (char*) c->dWave;
+	auto take = [&](size_t bytes) { char* r = b; b += (bytes + 255) & ~(size_t) 255; return r; };
+	const size_t rays = (size_t) c->waveRayCap * 2;
+	w.rayO = (float4*) take(rays * sizeof(float4));
+	w.rayD = (float4*) take(rays * sizeof(float4));
+	w.rayW = (float4*) take(rays * sizeof(float4));
+	w.rayC = (uint2*) take(rays * sizeof(uint2));
+	w.hitA = (float4*) take((size_t) c->waveHitCap * sizeof(float4));
+	w.hitB = (int2*) take((size_t) c->waveHitCap * sizeof(int2));
+	w.litA = (float4*) take((size_t) c->waveLitCap * sizeof(float4));
+	w.litB = (float4*) take((size_t) c->waveLitCap * sizeof(float4));
+	w.litC = (float4*) take((size_t) c->waveLitCap * sizeof(float4));
+	w.litD = (uint2*) take((size_t) c->waveLitCap * sizeof(uint2));
+	w.litE = (float4*) take((size_t) c->waveLitCap * sizeof(float4));
+	w.litF = (float4*) take((size_t) c->waveLitCap * sizeof(float4));
+	w.acc = (long long*) take((size_t) c->width * c->height * 3 * sizeof(long long));
+	w.rayCap = c->waveRayCap;
+	w.litCap = c->waveLitCap;
+	w.litPerRay = c->waveLitPerRay;
+	w.ctr = c->dWaveCtr;
+}
+
+static int renderWave(FrayGpuCtx* c, const RenderParams& rp, float* dOut, cudaStream_t stream, bool timed)
+{
+	WaveParams w;
+	memset(&w, 0, sizeof(w));
+	w.rp = rp;
+	w.rp.out = dOut;
+	w.numSamples = rp.s1 - rp.s0;
+	w.invNumSamples = 1.0f / (float) w.numSamples;
+	const double prim = (double) rp.numOwnedTiles * 32.0 * w.numSamples;
+	if (prim >= 4.0e9) return fail(FRAY_GPU_EINVAL, "more than 2^32 primary samples in one call");
+	w.numPrimary = (unsigned) prim;
+	w.rp.exactDiv = (prim / 32.0 >= 4e6 || rp.exactDiv) ? 1 : 0;
+	int rc = waveAllocate(c, w.numPrimary);
+	if (rc != FRAY_GPU_OK) return rc;
+	waveLayout(c, w);
+	const bool stereo = c->sc32.cam.stereoSep > 0;
+	c->waveCfg.numSMs = c->numSMs;
+	c->waveCfg.stream = stream;
+	// the right eye of a stereo pair is queued by the left eye's SHADE (it continues the left eye's random stream): one more wave
+	c->waveCfg.waves = std::min(FRAY_WAVE_MAX, (c->waveSecondary ? c->sc32.maxTraceDepth + 1 : 1) + (stereo ? 1 : 0));
+	if (c->waveCfg.waves < 1) c->waveCfg.waves = 1;
+	CUDA_TRY(cudaMemsetAsync(c->dWaveCtr, 0, FRAY_WCTR_COUNT * sizeof(unsigned), stream));
+	if (timed) CUDA_TRY(cudaEventRecord(c->evStart, stream));
+	CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t) c->width * c->height * 3 * sizeof(long long), stream));
+	cudaError_t e = launchWaveFrame(c->sc32, w, c->features, c->waveCfg);
+	if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("wavefront kernel launch: ") + cudaGetErrorString(e));
+	c->launches = c->waveCfg.waves * (c->sc32.numLights > 0 ? 3 : 2) + 1;
+	if (timed) CUDA_TRY(cudaEventRecord(c->evStop, stream));
+	c->pendingStats = timed;
+	c->lastStream = stream;
+	c->waveLast = true;
+	return FRAY_GPU_OK;
+}
+
+static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStream_t stream, bool timed);
+
+// After a wavefront frame: wait for it and, if a queue overflowed, double the queues and render the frame again.
+static int waveFinish(FrayGpuCtx* c)
+{
+	for (int attempt = 0; c->waveLast && attempt < 12; attempt++) {
+		CUDA_TRY(cudaStreamSynchronize(c->lastStream ? c->lastStream : c->stream));
+		unsigned overflow = 0;
+		CUDA_TRY(cudaMemcpy(&overflow, c->dWaveCtr + FRAY_WCTR_OVERFLOW, sizeof(unsigned), cudaMemcpyDeviceToHost));
+		if (!overflow) return FRAY_GPU_OK;
+		if (c->waveRayCap >= 600000000u) return fail(FRAY_GPU_ENOMEM, "the ray tree of this frame does not fit the wavefront queues");
+		c->waveRayCap = (unsigned) std::min(2.0 * c->waveRayCap, 6.0e8);
+		const FrayGpuFrame f = c->lastFrame;
+		int rc = renderInto(c, &f, c->lastOut, c->lastStream, c->lastTimed);
+		if (rc != FRAY_GPU_OK) return rc;
+	}
+	return FRAY_GPU_OK;
 }
 
 static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStream_t stream, bool timed)
@@ -321,6 +484,11 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	CUDA_TRY(cudaMemsetAsync(c->dWork, 0, sizeof(unsigned int), stream));
 
 	c->launches = 0;
+	c->waveLast = false;
+	c->lastFrame = *f;
+	c->lastOut = dOut;
+	c->lastTimed = timed;
+	if (waveEligible(c, f) && ownedTiles > 0 && s1 > s0) return renderWave(c, p, dOut, stream, timed);
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStart, stream));
 	if (ownedTiles > 0 && (s1 > s0 || f->mode == FRAY_RENDER_AOV)) {
 		cudaError_t e = c->precision == FRAY_GPU_FP32 ? launchRender<float>(c->sc32, p, c->features, f->mode, cfg)
@@ -343,6 +511,8 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 
 static int fetchStats(FrayGpuCtx* c, FrayGpuStats* stats)
 {
+	int wrc = waveFinish(c);
+	if (wrc != FRAY_GPU_OK) return wrc;
 	CUDA_TRY(cudaStreamSynchronize(c->lastStream ? c->lastStream : c->stream));
 	unsigned long long h[3] = { 0, 0, 0 };
 	int err = 0;
@@ -371,6 +541,8 @@ int fray_gpu_render(FrayGpuCtx* c, const FrayGpuFrame* frame, float* rgb_out, Fr
 {
 	if (!c || !frame || !rgb_out) return fail(FRAY_GPU_EINVAL, "null argument");
 	int rc = renderInto(c, frame, c->dFrame, c->stream, true);
+	if (rc != FRAY_GPU_OK) return rc;
+	rc = waveFinish(c); // wavefront frames: a full queue means the frame is rendered again before it is copied out
 	if (rc != FRAY_GPU_OK) return rc;
 	const size_t bytes = (size_t) c->width * c->height * 3 * sizeof(float);
 	// straight into the caller's buffer when it is page-locked (e.g. a pinned torch tensor), else through our pinned staging buffer

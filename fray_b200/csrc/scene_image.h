@@ -823,6 +823,43 @@ template <typename R> struct SceneImage {
 			o.inFlat = 0;
 			o.pad[0] = o.pad[1] = o.pad[2] = 0;
 		}
+		// world-space boxes of the nodes (fast precision, wave.cuh): the eight corners of the object-space bounds through the node transform
+		std::vector<float4> nodeBox;
+		if (!Num<R>::kExact) {
+			nodeBox.resize(2 * (size_t) s.num_nodes);
+			for (int i = 0; i < s.num_nodes; i++) {
+				const FrayGpuNode& n = s.nodes[i];
+				const FrayGpuGeometry& g = s.geometries[n.geometry];
+				double lo[3] = { -1e30, -1e30, -1e30 }, hi[3] = { 1e30, 1e30, 1e30 };
+				bool bounded = true;
+				if (g.type == FRAY_GEOM_MESH) {
+					for (int k = 0; k < 3; k++) { lo[k] = s.meshes[g.mesh].bbox_min[k]; hi[k] = s.meshes[g.mesh].bbox_max[k]; }
+				} else if (g.type == FRAY_GEOM_SPHERE || g.type == FRAY_GEOM_CUBE) {
+					for (int k = 0; k < 3; k++) { lo[k] = g.p[k] - g.p[3]; hi[k] = g.p[k] + g.p[3]; }
+				} else if (g.type == FRAY_GEOM_PLANE && g.p[1] < 1e15) {
+					lo[0] = lo[2] = -g.p[1]; hi[0] = hi[2] = g.p[1]; lo[1] = hi[1] = g.p[0];
+				} else {
+					bounded = false; // CSG, unbounded planes: never culled
+				}
+				double wlo[3] = { 1e30, 1e30, 1e30 }, whi[3] = { -1e30, -1e30, -1e30 };
+				if (bounded) {
+					for (int c = 0; c < 8; c++) {
+						const D3 p{ (c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2] };
+						const D3 w = rowMul(p, n.T.m);
+						const double q[3] = { w.x + n.T.offset[0], w.y + n.T.offset[1], w.z + n.T.offset[2] };
+						for (int k = 0; k < 3; k++) { wlo[k] = std::min(wlo[k], q[k]); whi[k] = std::max(whi[k], q[k]); }
+					}
+					double ext = 0;
+					for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(wlo[k]), std::fabs(whi[k])));
+					const double pad = 1e-4 * ext + 1e-4;
+					for (int k = 0; k < 3; k++) { wlo[k] -= pad; whi[k] += pad; }
+				} else {
+					for (int k = 0; k < 3; k++) { wlo[k] = -3e38; whi[k] = 3e38; }
+				}
+				nodeBox[2 * i] = float4{ (float) std::max(wlo[0], -3e38), (float) std::max(wlo[1], -3e38), (float) std::max(wlo[2], -3e38), 0.0f };
+				nodeBox[2 * i + 1] = float4{ (float) std::min(whi[0], 3e38), (float) std::min(whi[1], 3e38), (float) std::min(whi[2], 3e38), 0.0f };
+			}
+		}
 		// feature bits this scene needs from the kernels
 		// textures count only if something that is rendered refers to one (smallpt.fray defines a Fresnel texture and a Layered
 		// shader that no node uses)
@@ -909,6 +946,7 @@ template <typename R> struct SceneImage {
 		FRAY_PUT(texels, texels);
 		FRAY_PUT(kdTris, kdTris);
 		FRAY_PUT(lightRecs, lightRecs);
+		FRAY_PUT(nodeBox, nodeBox);
 		FRAY_PUT(flatPolys, flatPolys);
 		FRAY_PUT(flatInfo, flatInfo);
 #undef FRAY_PUT
@@ -926,7 +964,7 @@ template <typename R> struct SceneImage {
 		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
 		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
 		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
-		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(lightRecs);
+		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(lightRecs); FRAY_REBASE(nodeBox);
 #undef FRAY_REBASE
 		return d;
 	}

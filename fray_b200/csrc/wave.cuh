@@ -12,9 +12,9 @@
 //           constant, environment, emission), (b) one LIT record per Lambert / Phong evaluation -- the point, the normal, the
 //           colours: everything the light loop needs except visibility, (c) the secondary rays, appended to the next wave's
 //           queue through warp-aggregated atomics.
-//   SHADOW  one thread per (lit record, light sample): regenerates the sample point from the counter-based stream (the
-//           stream position of sample k is known: c0 + 2k, src/lights.cpp:49-77 draws two floats per sample), any-hit
-//           traversal, and the Lambert / Phong term if the light is visible. There is NO shadow-ray queue.
+//   SHADOW  one thread per lit record: the light loop. The sample points come from the record's counter-based stream (the
+//           record carries the stream position of its first draw), every sample is one any-hit traversal, and the Lambert /
+//           Phong term is evaluated only if the light is visible. There is NO shadow-ray queue.
 //
 // Radiance is accumulated per pixel in 64-bit fixed point (2^-32): integer addition is associative, so the frame is
 // independent of the order in which threads, warps or GPUs deliver their terms -- bit-identical run to run, and tile or
@@ -237,6 +237,66 @@ FRAY_HD void waveLocalRay(const DNode<float>& nd, const Ray<float>& ray, Ray<flo
 	scale = l2 * rl;
 }
 
+// does the world ray touch the box within [0, tMax] ? (DScene::nodeBox: padded, so "no" is safe)
+FRAY_HD bool waveBoxHit(const float4 lo, const float4 hi, const Ray<float>& ray, const V3<float>& inv, float tMax)
+{
+	const float ax0 = (lo.x - ray.start.x) * inv.x, ax1 = (hi.x - ray.start.x) * inv.x;
+	const float ay0 = (lo.y - ray.start.y) * inv.y, ay1 = (hi.y - ray.start.y) * inv.y;
+	const float az0 = (lo.z - ray.start.z) * inv.z, az1 = (hi.z - ray.start.z) * inv.z;
+	const float tn = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+	const float tf = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tMax));
+	return tn <= tf;
+}
+
+// The node loop of raytrace() / visible() (src/main.cpp:64-80, 250-258) with Node::intersect (src/geometry.cpp:196-208): nodes
+// whose padded world box (DScene::nodeBox) the ray misses are skipped before their ray transform; meshes go through kdWalk.
+// CLOSEST: wh holds the best hit so far (from the flat table) and is improved. ANY: true as soon as something lies within
+// maxDist (wh is not touched).
+// (Measured alternative: the node loop folded INTO the walk as one while-while state machine, so that lanes walking different
+// nodes share instructions. With the 3-7 nodes of the bundled scenes it was slower -- boxed shadow pass 2.99 -> 3.20 ms: every
+// trip then pays for the node set-up block with one or two lanes active, while here all lanes set a node up together.)
+template <bool ANYHIT, int F, typename STK>
+FRAY_HD_HOT bool waveNodes(const DScene<float>& sc, const Ray<float>& ray, float maxDist, int origin, STK& stk, WaveHit& wh)
+{
+	// RRay::prepareForTracing, src/bbox.h:49-54, for the world ray
+	const V3<float> inv(fabsf(ray.dir.x) > 1e-12f ? 1.0f / ray.dir.x : 1e12f, fabsf(ray.dir.y) > 1e-12f ? 1.0f / ray.dir.y : 1e12f,
+	                    fabsf(ray.dir.z) > 1e-12f ? 1.0f / ray.dir.z : 1e12f);
+	for (int n = 0; n < sc.numNodes; n++) {
+		const DNode<float>& nd = sc.nodes[n];
+		if ((F & FRAY_F_FLAT) && nd.inFlat) continue;
+		if (!waveBoxHit(sc.nodeBox[2 * n], sc.nodeBox[2 * n + 1], ray, inv, ANYHIT ? maxDist : wh.t)) continue;
+		Ray<float> local;
+		float scale;
+		waveLocalRay(nd, ray, local, scale);
+		const DGeom<float>& g = sc.geoms[nd.geom];
+		// hits farther than the best so far may be dropped (the reference compares afterwards, src/main.cpp:256)
+		const float maxT = ANYHIT ? maxDist * scale : (wh.t < Num<float>::big() / 4 ? wh.t * scale * 1.0001f : Num<float>::big());
+		float tObj, l2 = 0, l3 = 0;
+		int tri = -1;
+		V3<float> ipObj;
+		if (g.type == FRAY_GEOM_MESH) {
+			if (!kdWalk<ANYHIT>(sc, sc.meshes[g.mesh], local, maxT, stk, tObj, tri, l2, l3)) continue;
+			ipObj = local.start + local.dir * tObj;
+		} else {
+			Hit<float> h;
+			if (!intersectAnalytic(sc, nd.geom, local, h, false, n == origin)) continue;
+			ipObj = h.ip;
+		}
+		const float tw = dist3(ray.start, xfPoint(nd.T, ipObj)); // info.dist of Node::intersect, src/geometry.cpp:203
+		if (ANYHIT) {
+			if (tw < maxDist) return true;
+		} else if (tw < wh.t) {
+			wh.t = tw;
+			wh.node = n;
+			wh.tri = tri;
+			wh.l2 = l2;
+			wh.l3 = l3;
+			wh.flat = -1;
+		}
+	}
+	return false;
+}
+
 // the closest-hit loops of raytrace(), src/main.cpp:250-271: ids and distance only, attributes are SHADE's business
 template <int F, typename STK>
 FRAY_HD_HOT void waveClosest(const DScene<float>& sc, const FlatTab& ft, const Ray<float>& ray, int origin, STK& stk, WaveHit& wh)
@@ -258,36 +318,7 @@ FRAY_HD_HOT void waveClosest(const DScene<float>& sc, const FlatTab& ft, const R
 			wh.node = (fi.flags & FRAY_FLAT_LIGHT) ? -2 - fi.node : fi.node;
 		}
 	}
-	for (int n = 0; n < sc.numNodes; n++) {
-		const DNode<float>& nd = sc.nodes[n];
-		if ((F & FRAY_F_FLAT) && nd.inFlat) continue;
-		Ray<float> local;
-		float scale;
-		waveLocalRay(nd, ray, local, scale);
-		const DGeom<float>& g = sc.geoms[nd.geom];
-		// hits farther than the best so far may be dropped (the reference compares afterwards, src/main.cpp:256)
-		const float maxT = wh.t < Num<float>::big() / 4 ? wh.t * scale * 1.0001f : Num<float>::big();
-		float tObj, l2 = 0, l3 = 0;
-		int tri = -1;
-		V3<float> ipObj;
-		if (g.type == FRAY_GEOM_MESH) {
-			if (!kdWalk<false>(sc, sc.meshes[g.mesh], local, maxT, stk, tObj, tri, l2, l3)) continue;
-			ipObj = local.start + local.dir * tObj;
-		} else {
-			Hit<float> h;
-			if (!intersectLeafGeom<float, false>(sc, nd.geom, local, maxT, h, false, false, n == origin)) continue;
-			ipObj = h.ip;
-		}
-		const float tw = dist3(ray.start, xfPoint(nd.T, ipObj)); // info.dist of Node::intersect, src/geometry.cpp:203
-		if (tw < wh.t) {
-			wh.t = tw;
-			wh.node = n;
-			wh.tri = tri;
-			wh.l2 = l2;
-			wh.l3 = l3;
-			wh.flat = -1;
-		}
-	}
+	waveNodes<false, F>(sc, ray, 0.0f, origin, stk, wh);
 	if (!(F & FRAY_F_FLAT) || !sc.lightsInFlat) {
 		for (int l = 0; l < sc.numLights; l++) {
 			float d;
@@ -301,7 +332,7 @@ FRAY_HD_HOT void waveClosest(const DScene<float>& sc, const FlatTab& ft, const R
 	}
 }
 
-// visible(), src/main.cpp:64-80, over the short stack (cf. visible() in core.cuh)
+// visible(), src/main.cpp:64-80 (cf. visible() in core.cuh)
 template <int F, typename STK>
 FRAY_HD_HOT bool waveVisible(const DScene<float>& sc, const FlatTab& ft, const V3<float>& a, const V3<float>& b, int light, int origin, STK& stk)
 {
@@ -324,28 +355,8 @@ FRAY_HD_HOT bool waveVisible(const DScene<float>& sc, const FlatTab& ft, const V
 		if ((F & FRAY_F_SPHERES) && flatSpheresAny(ft.spheres, sc.numFlatSpheres, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 		if ((F & FRAY_F_TWOSIDED) && flatAny2(ft.polys2, sc.numFlat2, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 	}
-	for (int n = 0; n < sc.numNodes; n++) {
-		const DNode<float>& nd = sc.nodes[n];
-		if ((F & FRAY_F_FLAT) && nd.inFlat) continue;
-		Ray<float> local;
-		float scale;
-		waveLocalRay(nd, ray, local, scale);
-		const DGeom<float>& g = sc.geoms[nd.geom];
-		const float maxT = maxDist * scale;
-		V3<float> ipObj;
-		if (g.type == FRAY_GEOM_MESH) {
-			float tObj, l2, l3;
-			int tri;
-			if (!kdWalk<true>(sc, sc.meshes[g.mesh], local, maxT, stk, tObj, tri, l2, l3)) continue;
-			ipObj = local.start + local.dir * tObj;
-		} else {
-			Hit<float> h;
-			if (!intersectLeafGeom<float, true>(sc, nd.geom, local, maxT, h, false, false, n == origin)) continue;
-			ipObj = h.ip;
-		}
-		if (dist3(ray.start, xfPoint(nd.T, ipObj)) < maxDist) return false;
-	}
-	return true;
+	WaveHit unused;
+	return !waveNodes<true, F>(sc, ray, maxDist, origin, stk, unused);
 }
 
 // ---- SHADE -----------------------------------------------------------------------------------------------------------------
@@ -385,7 +396,7 @@ FRAY_HD void waveHitAttributes(const DScene<float>& sc, const FlatTab& ft, const
 	Ray<float> local;
 	float scale;
 	waveLocalRay(nd, ray, local, scale);
-	if (!intersectLeafGeom<float, false>(sc, nd.geom, local, Num<float>::big(), h, nd.needsUV != 0, true, wh.node == r.origin)) {
+	if (!intersectAnalytic(sc, nd.geom, local, h, nd.needsUV != 0, wh.node == r.origin)) {
 		h.ip = local.start + local.dir * (wh.t * scale); // cannot happen (TRACE just found it); keep the numbers finite
 		h.norm = V3<float>(0, 1, 0);
 	}
@@ -519,42 +530,47 @@ FRAY_HD void waveShade(const DScene<float>& sc, const FlatTab& ft, const WaveRay
 }
 
 // ---- SHADOW ----------------------------------------------------------------------------------------------------------------
-// Sample `ordinal` (0 .. sc.lightSamples-1, lights in order, samples in order) of the light loop of one lit record: the term
-// Lambert::shade / Phong::shade add for it (src/shading.cpp:55-78, 108-141), already divided by the light's sample count.
-// Returns black when the light is not visible. `traced` is set when a shadow ray was shot.
+// The light loop of Lambert::shade / Phong::shade (src/shading.cpp:55-78, 108-141) for one lit record: every light, every
+// sample of it in order -- the sample point from the record's random stream (RectLight::getNthSample draws two floats per
+// sample, src/lights.cpp:49-77; the stream position of the record's first draw is L.count), the shadow ray, and the Lambert /
+// Phong term when the light is visible. One thread owns a record, so the lanes of a warp -- 32 neighbouring hit points -- shoot
+// at the SAME light sample at the same time and walk the same parts of the scene (32 samples of one point on 32 lanes, which
+// was the first version, kept ~10 lanes busy in the KD walks). Returns the sum the shader adds to its ambient term.
 template <int F, typename STK>
-FRAY_HD_HOT Col waveLightSample(const DScene<float>& sc, const FlatTab& ft, const WaveLit& L, int ordinal, const uint32_t* keys, uint32_t seed, STK& stk)
+FRAY_HD_HOT Col waveLightLoop(const DScene<float>& sc, const FlatTab& ft, const WaveLit& L, const uint32_t* keys, uint32_t seed, STK& stk, unsigned& shadowRays)
 {
-	int li = 0, si = ordinal;
-	uint32_t draws = 0;
-	for (;; li++) {
-		const int ns = lightNumSamples(sc.lights[li]);
-		if (si < ns) break;
-		si -= ns;
-		if (sc.lights[li].type == FRAY_LIGHT_RECT) draws += 2u * (uint32_t) ns;
-	}
-	const DLight<float>& light = sc.lights[li];
 	RngT<FRAY_RNG_KEYED> rng;
 	rng.keys = keys;
 	rng.init(seed, (uint32_t) L.pixel, (uint32_t) L.sample, L.branch);
-	if (light.type == FRAY_LIGHT_RECT) rng.skip(L.count + draws + 2u * (uint32_t) si);
-	Col lightCol;
-	V3<float> lightPos;
-	lightSample(light, rng, si, L.ip, lightPos, lightCol, true);
+	rng.skip(L.count);
 	const V3<float> shadowStart = L.ip + L.n * Num<float>::offsetEps(maxAbs(L.ip));
-	if (!waveVisible<F>(sc, ft, shadowStart, lightPos, li, L.origin, stk)) return Col(0, 0, 0);
-	const V3<float> toL = lightPos - L.ip;
-	const float distSqr = lengthSqr(toL);
-	const V3<float> toLight = normalized(toL);
-	const float cosAngle = dot(toLight, L.n);
-	const float lambertTerm = fmaxf(0.0f, cosAngle / distSqr);
-	Col c = L.diffuse * lightCol * lambertTerm;
-	if (L.phong) {
-		const V3<float> rr = reflect(-toLight, L.n);
-		const float cosRefl = dot(-L.rayDir, rr);
-		if (cosRefl > 0) c = c + lightCol / distSqr * L.specular * Num<float>::powR(cosRefl, L.exponent);
+	Col result(0, 0, 0);
+	for (int li = 0; li < sc.numLights; li++) {
+		const DLight<float>& light = sc.lights[li];
+		const int ns = lightNumSamples(light);
+		Col sum(0, 0, 0);
+		for (int si = 0; si < ns; si++) {
+			Col lightCol;
+			V3<float> lightPos;
+			lightSample(light, rng, si, L.ip, lightPos, lightCol, true);
+			shadowRays++;
+			if (!waveVisible<F>(sc, ft, shadowStart, lightPos, li, L.origin, stk)) continue;
+			const V3<float> toL = lightPos - L.ip;
+			const float distSqr = lengthSqr(toL);
+			const V3<float> toLight = normalized(toL);
+			const float cosAngle = dot(toLight, L.n);
+			const float lambertTerm = fmaxf(0.0f, cosAngle / distSqr);
+			Col c = L.diffuse * lightCol * lambertTerm;
+			if (L.phong) {
+				const V3<float> rr = reflect(-toLight, L.n);
+				const float cosRefl = dot(-L.rayDir, rr);
+				if (cosRefl > 0) c = c + lightCol / distSqr * L.specular * Num<float>::powR(cosRefl, L.exponent);
+			}
+			sum = sum + c;
+		}
+		result = result + sum / (float) ns;
 	}
-	return c / (float) lightNumSamples(light);
+	return result;
 }
 
 // ---- the camera ray of primary sample (pixel, s) and the state its raytrace() starts in (src/main.cpp:296-321, 348-359) ---

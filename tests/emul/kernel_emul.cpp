@@ -169,14 +169,14 @@ static void renderWaveT(const DScene<float>& sc, const FlatTab& ft, const FrayGp
 				sink.ray(rightEyes[i]);
 			}
 		}
-		for (const WaveLit& L: lits)
-			for (int k = 0; k < sc.lightSamples; k++) {
-				WaveRay tag;
-				tag.pixel = L.pixel; tag.eye = L.eye;
-				sink.add(tag, waveLightSample<F>(sc, ft, L, k, keys, fr.seed, stk));
-				cnt.rays++;
-				cnt.shadow++;
-			}
+		for (const WaveLit& L: lits) {
+			WaveRay tag;
+			tag.pixel = L.pixel; tag.eye = L.eye;
+			unsigned shot = 0;
+			sink.add(tag, waveLightLoop<F>(sc, ft, L, keys, fr.seed, stk, shot));
+			cnt.rays += shot;
+			cnt.shadow += shot;
+		}
 		cur.swap(next);
 	}
 	for (size_t p = 0; p < (size_t) W * H; p++)

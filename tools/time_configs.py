@@ -18,15 +18,19 @@ def main():
         ("boxed", None, None),
         ("zaphod", None, None),
         ("forest", dict(interactive="off", frameWidth=1920, frameHeight=1080), None),
+        ("forest", dict(interactive="off", frameWidth=3840, frameHeight=2160), None),
+        ("forest", dict(interactive="off", frameWidth=3840, frameHeight=2160, wantAA="on"), None),
         ("hw9/dragon", None, None),
     ]
     for name, st, cam in timing:
         f = scenes.override_scene(name, "time", st, cam)
         sc = fb.Scene(f)
         for prec, pn in ((fb.FP32, "f32"), (fb.FP64, "f64")):
+            if "--fp32" in sys.argv and prec != fb.FP32:
+                continue
             ctx = fb.GpuContext(sc, 0, prec)
             best = None
-            for it in range(3):
+            for it in range(5):
                 img, s = ctx.render()
                 best = s if best is None or s.device_ms < best.device_ms else best
             print(f"TIME {name:14s} {pn} {sc.width}x{sc.height} spp {sc.spp}: {best.device_ms:9.2f} ms  rays {best.rays} "
