@@ -25,6 +25,7 @@ FP32 = 0
 FP64 = 1
 RENDER_BEAUTY = 0
 RENDER_AOV = 1
+RENDER_PREPASS = 2
 FRAME_SUM = 1
 FRAME_OWNED_ONLY = 2
 FRAME_SAMPLE_RANGE = 4
@@ -137,6 +138,11 @@ def gpu_lib() -> C.CDLL:
         L.fray_gpu_sync.argtypes = [C.c_void_p, C.POINTER(FrayStats)]
         L.fray_gpu_destroy.argtypes = [C.c_void_p]
         L.fray_gpu_measure_peaks.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.fray_gpu_multi_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.fray_gpu_multi_device_count.argtypes = [C.c_void_p]
+        L.fray_gpu_multi_update_camera.argtypes = [C.c_void_p, C.POINTER(FrayCamera)]
+        L.fray_gpu_multi_render.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_int, C.c_void_p, C.POINTER(FrayStats)]
+        L.fray_gpu_multi_destroy.argtypes = [C.c_void_p]
         _gpu = L
     return _gpu
 
@@ -276,6 +282,50 @@ class GpuContext:
         stats = FrayStats()
         self._check(self._lib.fray_gpu_sync(self._ctx, C.byref(stats)), "fray_gpu_sync")
         return RenderStats.of(stats)
+
+
+SPLIT_AUTO, SPLIT_TILES, SPLIT_SAMPLES = 0, 1, 2
+MULTI_FAST = 0x100
+
+
+class MultiGpuContext:
+    """``fray_gpu_multi_create`` .. ``fray_gpu_multi_destroy``: one scene on several CUDA devices of this node, driven by this
+    one process (what ``pool.run(&worker, numThreads)`` is to the reference's host threads, src/main.cpp:402-404)."""
+
+    def __init__(self, scene: Scene, devices, precision: int = FP32):
+        self._lib = gpu_lib()
+        self.scene = scene
+        devs = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        ctx = C.c_void_p()
+        rc = self._lib.fray_gpu_multi_create(scene.flat, len(devs), arr, precision, C.byref(ctx))
+        if rc != 0:
+            raise FrayError(f"fray_gpu_multi_create failed ({rc}): {self._lib.fray_gpu_last_error().decode(errors='replace')}")
+        self._ctx = ctx
+        self.devices = devs
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.fray_gpu_multi_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def update_camera(self, cam: FrayCamera):
+        if self._lib.fray_gpu_multi_update_camera(self._ctx, C.byref(cam)) != 0:
+            raise FrayError(f"fray_gpu_multi_update_camera failed: {self._lib.fray_gpu_last_error().decode(errors='replace')}")
+
+    def render(self, out: np.ndarray | None = None, split: int = SPLIT_AUTO, **frame_kw):
+        h, w = self.scene.height, self.scene.width
+        if out is None:
+            out = np.empty((h, w, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == h * w * 3
+        frame = make_frame(**frame_kw)
+        stats = FrayStats()
+        rc = self._lib.fray_gpu_multi_render(self._ctx, C.byref(frame), split, out.ctypes.data, C.byref(stats))
+        if rc != 0:
+            raise FrayError(f"fray_gpu_multi_render failed ({rc}): {self._lib.fray_gpu_last_error().decode(errors='replace')}")
+        return out, RenderStats.of(stats)
 
 
 def measure_peaks(device: int = 0, ms: float = 20.0) -> tuple[float, float]:

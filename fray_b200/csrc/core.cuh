@@ -1966,12 +1966,12 @@ template <typename RNG> FRAY_HD void sampleOffset(bool randomOffsets, int sample
 // through raytraceSinglePixel (src/main.cpp:304-321). Used by the AOV pass, the test emulator and as the
 // straight-line reference for the warp-scheduled kernels in render_kernels.cuh.
 template <typename R, int F>
-FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, int px, int py, int width, int sampleIdx, WhittedState<R>* ws, RayCounters& cnt)
+FRAY_HD Col renderSample(const DScene<R>& sc, const FlatTab& ft, uint32_t seed, int px, int py, int width, int sampleIdx, WhittedState<R>* ws, RayCounters& cnt, bool centred = false)
 {
 	Rng rng;
 	rng.init(seed, (uint32_t) (py * width + px), (uint32_t) sampleIdx, 0);
-	float ox, oy;
-	sampleOffset(sc.cam.dof || sc.gi, sampleIdx, rng, ox, oy);
+	float ox = 0, oy = 0;
+	if (!centred) sampleOffset(sc.cam.dof || sc.gi, sampleIdx, rng, ox, oy); // centred: the prepass shoots through (x, y) itself, src/main.cpp:386
 	// x + offsetX is evaluated in float in the reference (int + float), then widened to double
 	const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);
 	const bool stereo = (F & FRAY_F_LENS) && sc.cam.stereoSep > 0;

@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +70,7 @@ struct FrayGpuCtx {
 	FrayGpuFrame lastFrame = {};
 	float* lastOut = nullptr;
 	bool lastTimed = false;
+	int forceChunk = 0;             // > 0: samples per work item imposed by fray_gpu_multi_render (bit-identical tile shares)
 	int waveFan = 1;                // secondary rays one hit can spawn (glossy samples), for the first guess of the queue size
 	bool waveSecondary = false;     // some node's shader reflects or refracts: the ray tree is deeper than the camera rays
 	int waveLitPerRay = 1;          // Lambert / Phong evaluations one hit can ask for (through Layered shaders)
@@ -288,6 +292,17 @@ static int pow2Floor(int v)
 	return p;
 }
 
+// samples per work item (render_kernels.cuh) for a call that owns `ownedTiles` tiles and renders `samples` samples of each pixel
+static int chooseChunk(int ownedTiles, int samples, int gridBlocks)
+{
+	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) gridBlocks * 128.0);
+	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 32.0)));
+	const double maxChunks = std::max(1.0, 192e6 / ((double) std::max(ownedTiles, 1) * 32.0 * 12.0));
+	C = std::max(C, (int) ((samples + maxChunks - 1) / maxChunks));
+	if (const char* e = getenv("FRAY_GPU_CHUNK")) C = std::max(1, atoi(e)); // experiments only
+	return std::min(C, samples);
+}
+
 // ---- wavefront Whitted path ------------------------------------------------------------------------------------------------
 // Fast precision, Whitted integrator, a generic node loop (KD meshes / analytic primitives) and no CSG: wave_kernels.cuh.
 // FRAY_GPU_NO_WAVE=1 keeps such scenes on the megakernel (A/B timing).
@@ -417,7 +432,8 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	if (s0 == 0 && s1 == 0 && !(f->flags & FRAY_FRAME_SAMPLE_RANGE)) s1 = spp;
 	if (s0 < 0 || s1 < s0 || s1 > spp) return fail(FRAY_GPU_EINVAL, "sample range outside [0, spp]");
 	if (!randomOffsets && spp > 5) return fail(FRAY_GPU_EINVAL, "more than 5 samples need dof or gi (fixed AA table has 5 entries, src/main.cpp:55-61)");
-	if (f->mode != FRAY_RENDER_BEAUTY && f->mode != FRAY_RENDER_AOV) return fail(FRAY_GPU_EINVAL, "unknown render mode");
+	if (f->mode != FRAY_RENDER_BEAUTY && f->mode != FRAY_RENDER_AOV && f->mode != FRAY_RENDER_PREPASS) return fail(FRAY_GPU_EINVAL, "unknown render mode");
+	if (f->mode == FRAY_RENDER_PREPASS && f->bucket_count > 1) return fail(FRAY_GPU_EINVAL, "the prepass is not split into buckets");
 	const int bcount = f->bucket_count > 0 ? f->bucket_count : 1;
 	const int brank = f->bucket_count > 0 ? f->bucket_rank : 0;
 	if (brank < 0 || brank >= bcount) return fail(FRAY_GPU_EINVAL, "bucket_rank outside [0, bucket_count)");
@@ -436,6 +452,7 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	cfg.stream = stream;
 	cfg.gridBlocks = c->numSMs * occ; // persistent: every resident CTA slot of the chip, exactly once
 	if (f->mode == FRAY_RENDER_AOV) cfg.gridBlocks = c->numSMs * 8;
+	if (f->mode == FRAY_RENDER_PREPASS) cfg.gridBlocks = std::max(1, std::min(c->numSMs * 2, ((c->width + 15) / 16) * ((c->height + 15) / 16) / 128 + 1));
 
 	RenderParams p;
 	memset(&p, 0, sizeof(p));
@@ -447,12 +464,8 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	// share a frame. Measured on a 1/8 share of the headline frame (tools/share_time.py, 1.10 ms of work): C = 1 1.229 ms,
 	// C = 2 1.204 ms, C = 4 1.233 ms, C = 8 1.289 ms. The scratch buffer (one RGB sum per pixel and chunk) is kept below 192 MB
 	const int samples = std::max(1, s1 - s0);
-	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) cfg.gridBlocks * 128.0);
-	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 32.0)));
-	const double maxChunks = std::max(1.0, 192e6 / ((double) ownedTiles * 32.0 * 12.0));
-	C = std::max(C, (int) ((samples + maxChunks - 1) / maxChunks));
-	if (const char* e = getenv("FRAY_GPU_CHUNK")) C = std::max(1, atoi(e)); // experiments only
-	C = std::min(C, samples);
+	int C = chooseChunk(ownedTiles, samples, cfg.gridBlocks);
+	if (c->forceChunk > 0) C = std::min(c->forceChunk, samples);
 	p.chunk = C;
 	p.numChunks = (samples + C - 1) / C;
 	p.tilesX = tilesX;
@@ -490,12 +503,12 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	c->lastTimed = timed;
 	if (waveEligible(c, f) && ownedTiles > 0 && s1 > s0) return renderWave(c, p, dOut, stream, timed);
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStart, stream));
-	if (ownedTiles > 0 && (s1 > s0 || f->mode == FRAY_RENDER_AOV)) {
+	if (ownedTiles > 0 && (s1 > s0 || f->mode != FRAY_RENDER_BEAUTY)) {
 		cudaError_t e = c->precision == FRAY_GPU_FP32 ? launchRender<float>(c->sc32, p, c->features, f->mode, cfg)
 		                                                : launchRender<double>(c->sc64, p, c->features, f->mode, cfg);
 		if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
 		c->launches = 1;
-		if (p.numChunks > 1 && f->mode != FRAY_RENDER_AOV) {
+		if (p.numChunks > 1 && f->mode == FRAY_RENDER_BEAUTY) {
 			combineKernel<<<c->numSMs * 4, 256, 0, stream>>>(p);
 			CUDA_TRY(cudaGetLastError());
 			c->launches = 2;
@@ -748,6 +761,262 @@ int fray_gpu_sync(FrayGpuCtx* c, FrayGpuStats* stats)
 	if (!c) return fail(FRAY_GPU_EINVAL, "null argument");
 	CUDA_TRY(cudaSetDevice(c->device));
 	return fetchStats(c, stats);
+}
+
+
+// ---- several GPUs, one process ---------------------------------------------------------------------------------------------
+// The reference spreads a frame over its host threads with one call, pool.run(&worker, numThreads) (src/main.cpp:402-404); this
+// is that call for the GPUs of a node. One context per device, a host thread per context (enqueueing a share costs ~25 us of
+// API calls; in sequence that would be a fifth of an 8-GPU frame), device 0 owns the frame:
+//   tile split    share d = the 8x4 tiles t with t % n == d, all samples; its kernels store the finished pixels straight into
+//                 device 0's frame through peer access (NVLink), every share with the samples-per-item the single GPU would
+//                 use, so the frame is bit-identical to the single-GPU frame;
+//   sample split  share d = samples [d*spp/n, (d+1)*spp/n) of every pixel, written as partial sums into slot d of a buffer on
+//                 device 0 (peer stores again); device 0 adds the slots in order and divides. Equal to the single-GPU frame up
+//                 to the FP32 summation order of the path-traced kernels, exactly for the wavefront (integer accumulators).
+// No NCCL here: within one process, events order "share written" before "device 0 reads". (The one-process-per-GPU form with
+// an NCCL reduce is fray_b200/dist.py.)
+struct FrayGpuMulti {
+	std::vector<FrayGpuCtx*> ctx;
+	int width = 0, height = 0;
+	float* dPartials = nullptr; // device of ctx[0]: [n][height][width][3]
+	std::vector<cudaEvent_t> done;
+	// the job of the current frame, one entry per context
+	std::vector<FrayGpuFrame> frames;
+	std::vector<float*> outs;
+	std::vector<int> rcs;
+	std::vector<std::string> errs;
+	std::vector<FrayGpuStats> stats;
+	// worker threads
+	std::vector<std::thread> workers;
+	std::mutex m;
+	std::condition_variable cvGo, cvDone;
+	unsigned long long generation = 0;
+	int enqueued = 0, finished = 0;
+	bool quit = false;
+};
+
+__global__ void sumPartialsKernel(const float* __restrict__ partials, int n, size_t frameFloats, float* __restrict__ out, float divisor)
+{
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < frameFloats; i += (size_t) gridDim.x * blockDim.x) {
+		float sum = 0;
+		for (int d = 0; d < n; d++) sum += partials[(size_t) d * frameFloats + i]; // in share order: deterministic
+		out[i] = sum / divisor;
+	}
+}
+
+static void multiWorker(FrayGpuMulti* mg, int d)
+{
+	unsigned long long seen = 0;
+	for (;;) {
+		{
+			std::unique_lock<std::mutex> lk(mg->m);
+			mg->cvGo.wait(lk, [&] { return mg->quit || mg->generation != seen; });
+			if (mg->quit) return;
+			seen = mg->generation;
+		}
+		FrayGpuCtx* c = mg->ctx[d];
+		int rc = renderInto(c, &mg->frames[d], mg->outs[d], c->stream, true);
+		if (rc == FRAY_GPU_OK && c->waveLast) rc = waveFinish(c); // a full wavefront queue: the share is rendered again before anyone reads it
+		if (rc == FRAY_GPU_OK && cudaEventRecord(mg->done[d], c->stream) != cudaSuccess) rc = fail(FRAY_GPU_ECUDA, "cudaEventRecord failed");
+		if (rc != FRAY_GPU_OK) mg->errs[d] = g_lastError;
+		mg->rcs[d] = rc;
+		{
+			std::lock_guard<std::mutex> lk(mg->m);
+			mg->enqueued++;
+		}
+		mg->cvDone.notify_all();
+		if (rc == FRAY_GPU_OK) { // the share's statistics, while device 0 already assembles the frame
+			rc = fetchStats(c, &mg->stats[d]);
+			if (rc != FRAY_GPU_OK) { mg->errs[d] = g_lastError; mg->rcs[d] = rc; }
+		}
+		{
+			std::lock_guard<std::mutex> lk(mg->m);
+			mg->finished++;
+		}
+		mg->cvDone.notify_all();
+	}
+}
+
+void fray_gpu_multi_destroy(FrayGpuMulti* mg)
+{
+	if (!mg) return;
+	{
+		std::lock_guard<std::mutex> lk(mg->m);
+		mg->quit = true;
+	}
+	mg->cvGo.notify_all();
+	for (std::thread& t: mg->workers) t.join();
+	for (size_t d = 0; d < mg->ctx.size(); d++) {
+		if (mg->ctx[d]) {
+			cudaSetDevice(mg->ctx[d]->device);
+			if (d < mg->done.size() && mg->done[d]) cudaEventDestroy(mg->done[d]);
+		}
+	}
+	if (!mg->ctx.empty() && mg->ctx[0]) {
+		cudaSetDevice(mg->ctx[0]->device);
+		cudaFree(mg->dPartials);
+	}
+	for (FrayGpuCtx* c: mg->ctx) fray_gpu_destroy(c);
+	delete mg;
+}
+
+int fray_gpu_multi_create(const FrayGpuScene* scene, int n_devices, const int* devices, int precision, FrayGpuMulti** out)
+{
+	if (!scene || !out || n_devices < 1 || n_devices > 64) return fail(FRAY_GPU_EINVAL, "bad argument");
+	*out = nullptr;
+	FrayGpuMulti* mg = new FrayGpuMulti;
+	mg->width = scene->settings.frame_width;
+	mg->height = scene->settings.frame_height;
+	for (int d = 0; d < n_devices; d++) {
+		FrayGpuCtx* c = nullptr;
+		const int rc = fray_gpu_create(scene, devices ? devices[d] : d, precision, &c);
+		if (rc != FRAY_GPU_OK) {
+			const std::string msg = g_lastError;
+			fray_gpu_multi_destroy(mg);
+			return fail(rc, msg);
+		}
+		mg->ctx.push_back(c);
+	}
+	const int dev0 = mg->ctx[0]->device;
+	for (int d = 0; d < n_devices; d++) {
+		FrayGpuCtx* c = mg->ctx[d];
+		cudaSetDevice(c->device);
+		cudaEvent_t ev = nullptr;
+		if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+			fray_gpu_multi_destroy(mg);
+			return fail(FRAY_GPU_ECUDA, "cudaEventCreate failed");
+		}
+		mg->done.push_back(ev);
+		if (c->device != dev0) { // this device's kernels store into device 0's memory
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, c->device, dev0);
+			const cudaError_t e = can ? cudaDeviceEnablePeerAccess(dev0, 0) : cudaErrorPeerAccessUnsupported;
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+				cudaGetLastError();
+				fray_gpu_multi_destroy(mg);
+				return fail(FRAY_GPU_EUNSUPPORTED, "no peer access from device " + std::to_string(c->device) + " to device " + std::to_string(dev0));
+			}
+			cudaGetLastError();
+		}
+	}
+	mg->frames.resize(n_devices);
+	mg->outs.resize(n_devices);
+	mg->rcs.assign(n_devices, 0);
+	mg->errs.resize(n_devices);
+	mg->stats.resize(n_devices);
+	for (int d = 0; d < n_devices; d++) mg->workers.emplace_back(multiWorker, mg, d);
+	*out = mg;
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_multi_device_count(const FrayGpuMulti* mg) { return mg ? (int) mg->ctx.size() : 0; }
+
+int fray_gpu_multi_update_camera(FrayGpuMulti* mg, const FrayGpuCamera* cam)
+{
+	if (!mg || !cam) return fail(FRAY_GPU_EINVAL, "null argument");
+	for (FrayGpuCtx* c: mg->ctx) {
+		const int rc = fray_gpu_update_camera(c, cam);
+		if (rc != FRAY_GPU_OK) return rc;
+	}
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_multi_render(FrayGpuMulti* mg, const FrayGpuFrame* frame, int split, float* rgb_out, FrayGpuStats* stats)
+{
+	if (!mg || !frame || !rgb_out) return fail(FRAY_GPU_EINVAL, "null argument");
+	if (frame->bucket_count > 0 || (frame->flags & (FRAY_FRAME_OWNED_ONLY | FRAY_FRAME_SAMPLE_RANGE)) || frame->sample_begin != 0 || frame->sample_end != 0)
+		return fail(FRAY_GPU_EINVAL, "fray_gpu_multi_render splits the frame itself: pass a whole frame");
+	const int n = (int) mg->ctx.size();
+	FrayGpuCtx* c0 = mg->ctx[0];
+	if (frame->mode == FRAY_RENDER_PREPASS) return fray_gpu_render(c0, frame, rgb_out, stats); // a few thousand rays: one GPU
+	const int spp = frame->spp > 0 ? frame->spp : c0->defaultSpp;
+	const bool gi = c0->precision == FRAY_GPU_FP32 ? c0->sc32.gi : c0->sc64.gi;
+	if (split == FRAY_GPU_SPLIT_AUTO) split = (frame->mode == FRAY_RENDER_BEAUTY && spp >= 8 * n) ? FRAY_GPU_SPLIT_SAMPLES : FRAY_GPU_SPLIT_TILES;
+	if (split != FRAY_GPU_SPLIT_TILES && split != FRAY_GPU_SPLIT_SAMPLES) return fail(FRAY_GPU_EINVAL, "unknown split");
+	if (split == FRAY_GPU_SPLIT_SAMPLES && (spp < n || frame->mode != FRAY_RENDER_BEAUTY)) split = FRAY_GPU_SPLIT_TILES;
+	const size_t frameFloats = (size_t) mg->width * mg->height * 3;
+	CUDA_TRY(cudaSetDevice(c0->device));
+	if (split == FRAY_GPU_SPLIT_SAMPLES && !mg->dPartials) CUDA_TRY(cudaMalloc(&mg->dPartials, frameFloats * sizeof(float) * n));
+	// tile shares with the samples-per-item of the whole frame on one GPU: every pixel is then summed exactly as there
+	int chunk = 0;
+	if (split == FRAY_GPU_SPLIT_TILES && n > 1 && frame->mode == FRAY_RENDER_BEAUTY && !(frame->flags & FRAY_GPU_MULTI_FAST)) {
+		int& occ = gi ? c0->occGI : c0->occWhitted;
+		if (occ < 0) {
+			occ = c0->precision == FRAY_GPU_FP32 ? renderOccupancy<float>(c0->sc32, c0->features, gi) : renderOccupancy<double>(c0->sc64, c0->features, gi);
+			if (occ < 1) occ = 1;
+		}
+		const int tilesX = (mg->width + FRAY_TILE_W - 1) / FRAY_TILE_W, tilesY = (mg->height + FRAY_TILE_H - 1) / FRAY_TILE_H;
+		chunk = chooseChunk(tilesX * tilesY, spp, c0->numSMs * occ);
+	}
+	for (int d = 0; d < n; d++) {
+		FrayGpuFrame f = *frame;
+		f.flags &= ~FRAY_GPU_MULTI_FAST;
+		f.spp = spp;
+		if (split == FRAY_GPU_SPLIT_TILES) {
+			f.bucket_rank = d;
+			f.bucket_count = n;
+			if (n > 1) f.flags |= FRAY_FRAME_OWNED_ONLY;
+			mg->outs[d] = c0->dFrame;
+		} else {
+			f.sample_begin = (int) ((long long) d * spp / n);
+			f.sample_end = (int) ((long long) (d + 1) * spp / n);
+			f.flags |= FRAY_FRAME_SUM | FRAY_FRAME_SAMPLE_RANGE;
+			mg->outs[d] = mg->dPartials + (size_t) d * frameFloats;
+		}
+		mg->frames[d] = f;
+		mg->ctx[d]->forceChunk = chunk;
+	}
+	{
+		std::lock_guard<std::mutex> lk(mg->m);
+		mg->enqueued = mg->finished = 0;
+		mg->generation++;
+	}
+	mg->cvGo.notify_all();
+	{
+		std::unique_lock<std::mutex> lk(mg->m);
+		mg->cvDone.wait(lk, [&] { return mg->enqueued == n; });
+	}
+	int rc = FRAY_GPU_OK;
+	for (int d = 0; d < n && rc == FRAY_GPU_OK; d++)
+		if (mg->rcs[d] != FRAY_GPU_OK) rc = fail(mg->rcs[d], "share " + std::to_string(d) + ": " + mg->errs[d]);
+	if (rc == FRAY_GPU_OK) {
+		// device 0: wait for every share, assemble, copy out
+		cudaSetDevice(c0->device);
+		cudaError_t e = cudaSuccess;
+		for (int d = 0; d < n && e == cudaSuccess; d++) e = cudaStreamWaitEvent(c0->stream, mg->done[d], 0);
+		if (e == cudaSuccess && split == FRAY_GPU_SPLIT_SAMPLES) {
+			sumPartialsKernel<<<c0->numSMs * 4, 256, 0, c0->stream>>>(mg->dPartials, n, frameFloats, c0->dFrame, (frame->flags & FRAY_FRAME_SUM) ? 1.0f : (float) spp);
+			e = cudaGetLastError();
+		}
+		const size_t bytes = frameFloats * sizeof(float);
+		cudaPointerAttributes attr;
+		const bool pinned = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		if (e == cudaSuccess) e = cudaMemcpyAsync(pinned ? rgb_out : c0->hStaging, c0->dFrame, bytes, cudaMemcpyDeviceToHost, c0->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c0->stream);
+		if (e == cudaSuccess && !pinned) memcpy(rgb_out, c0->hStaging, bytes);
+		if (e != cudaSuccess) rc = fail(FRAY_GPU_ECUDA, std::string("assembling the frame: ") + cudaGetErrorString(e));
+	}
+	{
+		std::unique_lock<std::mutex> lk(mg->m);
+		mg->cvDone.wait(lk, [&] { return mg->finished == n; });
+	}
+	for (int d = 0; d < n; d++) mg->ctx[d]->forceChunk = 0;
+	for (int d = 0; d < n && rc == FRAY_GPU_OK; d++)
+		if (mg->rcs[d] != FRAY_GPU_OK) rc = fail(mg->rcs[d], "share " + std::to_string(d) + ": " + mg->errs[d]);
+	if (rc == FRAY_GPU_OK && stats) {
+		memset(stats, 0, sizeof(*stats));
+		for (int d = 0; d < n; d++) {
+			stats->rays += mg->stats[d].rays;
+			stats->primary_rays += mg->stats[d].primary_rays;
+			stats->shadow_rays += mg->stats[d].shadow_rays;
+			stats->kernel_launches += mg->stats[d].kernel_launches;
+			stats->device_ms = std::max(stats->device_ms, mg->stats[d].device_ms); // the slowest share
+		}
+		if (split == FRAY_GPU_SPLIT_SAMPLES) stats->kernel_launches += 1;
+	}
+	return rc;
 }
 
 } // extern "C"

@@ -296,6 +296,36 @@ __global__ void __launch_bounds__(128) aovKernel(const DScene<R> sc, const Rende
 	}
 }
 
+// FRAY_RENDER_PREPASS: the 16x16 preview of render(), src/main.cpp:376-391 -- one sample through the centre pixel of every
+// 16x16 square (raytraceSinglePixel(cx, cy), no sub-pixel offset), painted over the whole square. One thread per square.
+#define FRAY_PREPASS_SQUARE 16
+template <typename R, int F>
+__global__ void __launch_bounds__(128) prepassKernel(const DScene<R> sc, const RenderParams p)
+{
+	const FlatTab ft = stageFlat<R, F>(sc);
+	const int sx = (p.width + FRAY_PREPASS_SQUARE - 1) / FRAY_PREPASS_SQUARE, sy = (p.height + FRAY_PREPASS_SQUARE - 1) / FRAY_PREPASS_SQUARE;
+	WhittedState<R> ws;
+	ws.sp = 0;
+	ws.overflow = 0;
+	ws.rootPending = false;
+	RayCounters cnt = { 0, 0, 0 };
+	for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < sx * sy; q += gridDim.x * blockDim.x) {
+		const int x0 = (q % sx) * FRAY_PREPASS_SQUARE, y0 = (q / sx) * FRAY_PREPASS_SQUARE;
+		const int x1 = min(p.width, x0 + FRAY_PREPASS_SQUARE), y1 = min(p.height, y0 + FRAY_PREPASS_SQUARE);
+		const int cx = (x0 + x1) / 2, cy = (y0 + y1) / 2;
+		const Col c = renderSample<R, F>(sc, ft, p.seed, cx, cy, p.width, 0, &ws, cnt, true);
+		for (int y = y0; y < y1; y++)
+			for (int x = x0; x < x1; x++) {
+				float* o = p.out + 3 * ((size_t) y * p.width + x);
+				o[0] = c.r; o[1] = c.g; o[2] = c.b;
+			}
+	}
+	atomicAdd(p.counters + 0, (unsigned long long) cnt.rays);
+	atomicAdd(p.counters + 1, (unsigned long long) cnt.primary);
+	atomicAdd(p.counters + 2, (unsigned long long) cnt.shadow);
+	if (ws.overflow) atomicExch(p.errorFlag, 1);
+}
+
 struct LaunchConfig {
 	int gridBlocks; // persistent grid
 	cudaStream_t stream;
@@ -317,6 +347,7 @@ template <typename R, int I> struct VariantDispatch {
 		if ((need & ~F) != 0) return VariantDispatch<R, I + 1>::launch(sc, p, need, mode, cfg);
 		const size_t smem = (F & FRAY_F_FLAT) ? flatSmemBytes(sc) : 0;
 		if (mode == FRAY_RENDER_AOV) aovKernel<R, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
+		else if (mode == FRAY_RENDER_PREPASS) prepassKernel<R, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
 		else if (sc.gi) renderKernel<R, true, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
 		else renderKernel<R, false, F><<<cfg.gridBlocks, 128, smem, cfg.stream>>>(sc, p);
 		return cudaGetLastError();

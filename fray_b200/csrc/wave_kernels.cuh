@@ -338,9 +338,12 @@ __global__ void __launch_bounds__(128, 4) waveShadeKernel(const DScene<float> sc
 }
 
 // ---- SHADOW ----------------------------------------------------------------------------------------------------------------
-// one thread per lit record: its whole light loop (wave.cuh, waveLightLoop), one term delivered to the pixel's accumulator
-template <int F>
-__global__ void __launch_bounds__(128, 8) waveShadowKernel(const DScene<float> sc, const WaveParams p)
+// one thread per lit record: its whole light loop (wave.cuh, waveLightLoop), one term delivered to the pixel's accumulator.
+// Compiled for CTAS resident CTAs per SM: 8 (64 registers, ~260 bytes of spills inside the light loop) where a record means one
+// or two shadow rays and occupancy hides the record fetch, 6 (80 registers) where it means many (area lights: boxed 2.81 -> 2.51 ms,
+// while forest and dragon lose 2-3 % with it).
+template <int F, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) waveShadowKernel(const DScene<float> sc, const WaveParams p)
 {
 	const FlatTab ft = stageFlat<float, F>(sc);
 	KdStackShared stk = waveStack(p);
@@ -436,18 +439,23 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 	p.stackOffset = (unsigned) flat;
 	if (cfg.occTrace <= 0) {
 		cudaFuncSetAttribute(waveTraceKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
-		cudaFuncSetAttribute(waveShadowKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
+		cudaFuncSetAttribute(waveShadowKernel<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
+		cudaFuncSetAttribute(waveShadowKernel<F, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaFuncSetAttribute(waveShadeKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) flat);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occTrace, waveTraceKernel<F>, 128, flat + stack);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F>, 128, flat);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F>, 128, flat + stack);
+		if (sc.lightSamples >= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 6>, 128, flat + stack);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 8>, 128, flat + stack);
 		if (cfg.occTrace < 1 || cfg.occShade < 1 || cfg.occShadow < 1) return cudaErrorLaunchOutOfResources;
 	}
 	for (int w = 0; w < cfg.waves; w++) {
 		p.wave = w;
 		waveTraceKernel<F><<<cfg.numSMs * cfg.occTrace, 128, flat + stack, cfg.stream>>>(sc, p);
 		waveShadeKernel<F><<<cfg.numSMs * cfg.occShade, 128, flat, cfg.stream>>>(sc, p);
-		if (sc.numLights > 0) waveShadowKernel<F><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
+		if (sc.numLights > 0) {
+			if (sc.lightSamples >= 8) waveShadowKernel<F, 6><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
+			else waveShadowKernel<F, 8><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
+		}
 	}
 	resolveWaveKernel<<<cfg.numSMs * 4, 256, 0, cfg.stream>>>(p);
 	return cudaGetLastError();

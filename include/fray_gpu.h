@@ -251,8 +251,10 @@ enum {
 
 enum {
 	FRAY_RENDER_BEAUTY = 0, /* rgb_out: float[h][w][3] */
-	FRAY_RENDER_AOV = 1     /* rgb_out: float[h][w][3] = {node index (-1 miss, -2-k light k), triangle index or -1,
+	FRAY_RENDER_AOV = 1,    /* rgb_out: float[h][w][3] = {node index (-1 miss, -2-k light k), triangle index or -1,
 	                           world distance} of the un-jittered pin-hole ray through (x, y) */
+	FRAY_RENDER_PREPASS = 2 /* rgb_out: the 16x16 preview the reference paints before a frame (render(), src/main.cpp:376-391):
+	                           one sample through the centre pixel of every 16x16 square, the square filled with its colour */
 };
 
 #define FRAY_FRAME_SUM 1u   /* write per-pixel SUMS over the rendered samples instead of sum / spp */
@@ -326,6 +328,32 @@ int fray_gpu_resolve_device(FrayGpuCtx* ctx, const void* d_sum, void* d_rgb, int
 int fray_gpu_sync(FrayGpuCtx* ctx, FrayGpuStats* stats);
 
 void fray_gpu_destroy(FrayGpuCtx* ctx);
+
+/* ---- several GPUs of one node, one process -------------------------------------------------- */
+/* What pool.run(&worker, scene.settings.numThreads) is to the reference's host threads (src/main.cpp:402-404,
+ * src/cxxptl-sdl.cpp:285-318): one call renders the frame on `n_devices` GPUs. The scene is uploaded to each of
+ * `devices[0..n_devices)` (NULL = ordinals 0 .. n_devices-1; an ordinal may repeat); devices[0] owns the frame and every
+ * other device needs peer access to it (FRAY_GPU_EUNSUPPORTED otherwise). */
+typedef struct FrayGpuMulti FrayGpuMulti;
+
+enum {
+	FRAY_GPU_SPLIT_AUTO = 0,   /* samples while every GPU keeps >= 8 samples per pixel, else tiles */
+	FRAY_GPU_SPLIT_TILES = 1,  /* share d = the 8x4 pixel tiles t with t % n == d (the bucket list of src/sdl.cpp:243-262 dealt round
+	                              robin), stored straight into device 0's frame over NVLink; bit-identical to the single-GPU frame */
+	FRAY_GPU_SPLIT_SAMPLES = 2 /* share d = samples [d*spp/n, (d+1)*spp/n) of every pixel; partial sums are stored into device 0
+	                              and added there in share order (equal to the single-GPU frame up to FP32 summation order) */
+};
+#define FRAY_GPU_MULTI_FAST 0x100u /* frame flag, tile split only: let every share choose its own samples-per-item (a few
+                                      percent faster on small shares; the frame then equals the single-GPU frame only up to
+                                      FP32 summation order) */
+
+int fray_gpu_multi_create(const FrayGpuScene* scene, int n_devices, const int* devices, int precision, FrayGpuMulti** out);
+int fray_gpu_multi_device_count(const FrayGpuMulti* multi);
+int fray_gpu_multi_update_camera(FrayGpuMulti* multi, const FrayGpuCamera* camera);
+/* `frame` describes the WHOLE frame (no bucket / sample range); `split` is FRAY_GPU_SPLIT_*. Host buffer as fray_gpu_render().
+ * stats: rays summed over the shares, device_ms of the slowest share. */
+int fray_gpu_multi_render(FrayGpuMulti* multi, const FrayGpuFrame* frame, int split, float* rgb_out, FrayGpuStats* stats);
+void fray_gpu_multi_destroy(FrayGpuMulti* multi);
 
 /* Roofline denominators measured on the spot (bench.py): sustained FP32 FFMA rate of `device` in TFLOP/s (8 independent
  * FMA chains per thread, all SMs, ~`ms` milliseconds) and L2-resident read bandwidth in GB/s (a 32 MiB buffer read

@@ -36,12 +36,37 @@ def test_gpu_library_exports_header():
     assert lib.fray_gpu_abi_version() == 1
 
 
-def test_struct_layouts_match_header():
-    # sizes the ctypes mirrors must have for the by-pointer structs (checked against the C compiler once, here by arithmetic)
-    assert C.sizeof(fb.FrayFrame) == 32
-    assert C.sizeof(fb.FrayStats) == 40
-    assert C.sizeof(fb.FraySettings) == 40
-    assert C.sizeof(fb.FrayCamera) == 21 * 8 + 5 * 8 + 6 * 4 + 8
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of the by-pointer structs as the C COMPILER lays them out from include/fray_gpu.h, against the ctypes
+    mirrors in fray_b200/__init__.py (a C program is compiled and run; it also proves the header is plain C)."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text("""
+#include <stdio.h>
+#include <stddef.h>
+#include "fray_gpu.h"
+#define S(t) printf(#t " %zu\\n", sizeof(t))
+#define O(t, m) printf(#t "." #m " %zu\\n", offsetof(t, m))
+int main(void) {
+  S(FrayGpuFrame); S(FrayGpuStats); S(FrayGpuSettings); S(FrayGpuCamera); S(FrayGpuTransform); S(FrayGpuNode); S(FrayGpuGeometry);
+  S(FrayGpuMesh); S(FrayGpuKdNode); S(FrayGpuShader); S(FrayGpuLayer); S(FrayGpuTexture); S(FrayGpuBitmap); S(FrayGpuLight); S(FrayGpuScene);
+  O(FrayGpuFrame, flags); O(FrayGpuStats, device_ms); O(FrayGpuCamera, dof); O(FrayGpuCamera, left_mask); O(FrayGpuSettings, saturation);
+  return 0; }
+""")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", INCLUDE, str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    got = {k: int(v) for k, v in got.items()}
+    assert got["FrayGpuFrame"] == C.sizeof(fb.FrayFrame) == 32
+    assert got["FrayGpuStats"] == C.sizeof(fb.FrayStats) == 40
+    assert got["FrayGpuSettings"] == C.sizeof(fb.FraySettings) == 40
+    assert got["FrayGpuCamera"] == C.sizeof(fb.FrayCamera)
+    assert got["FrayGpuFrame.flags"] == fb.FrayFrame.flags.offset
+    assert got["FrayGpuStats.device_ms"] == fb.FrayStats.device_ms.offset
+    assert got["FrayGpuCamera.dof"] == fb.FrayCamera.dof.offset
+    assert got["FrayGpuCamera.left_mask"] == fb.FrayCamera.left_mask.offset
+    assert got["FrayGpuSettings.saturation"] == fb.FraySettings.saturation.offset
+    assert got["FrayGpuTransform"] == 21 * 8 and got["FrayGpuKdNode"] == 24 and got["FrayGpuBitmap"] == 16
 
 
 def test_no_cpu_fallback_without_device():

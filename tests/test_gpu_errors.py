@@ -46,3 +46,21 @@ def test_malformed_scene_is_rejected(golden_cases, data_dir):
             fb.GpuContext(sc, 0, fb.FP32)
     finally:
         head.abi_version = saved
+
+
+def test_an_empty_sample_share_renders_nothing(golden_cases, data_dir):
+    """FRAME_SAMPLE_RANGE makes [begin, end) literal: begin == end is an empty share (zeros, no rays), not "all samples" --
+    what a launcher computing r * spp / world gets when spp < world."""
+    path, seed = golden_scene(golden_cases, "cornell_box")
+    sc = fb.Scene(path)
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    full, fs = ctx.render(seed=seed, flags=fb.FRAME_SUM)
+    empty, es = ctx.render(seed=seed, flags=fb.FRAME_SUM, sample_begin=3, sample_end=3)
+    assert not empty.any() and es.rays == 0
+    zero, zs = ctx.render(seed=seed, flags=fb.FRAME_SUM, sample_begin=0, sample_end=0)
+    assert not zero.any() and zs.rays == 0
+    again, _ = ctx.render(seed=seed, flags=fb.FRAME_SUM)  # without the flag 0,0 still means everything
+    assert np.array_equal(again, full) and fs.rays > 0
+    ctx.close()
+    want, _ = ou.oracle_render(sc, seed=seed, flags=fb.FRAME_SUM, sample_begin=3, sample_end=3)
+    assert not want.any()
