@@ -388,6 +388,34 @@ def main():
                        "bit_identical": bool(np.array_equal(single, frame_np)), "frac_within_1e-5": float((d.max(axis=-1) <= 1e-5).mean()),
                        "note": "tile splits are bit-identical; a sample split regroups the FP32 partial sums of a pixel"}
 
+    # ---- multi-GPU, ONE process: fray_gpu_multi_render on the same N GPUs (the C++ drop-in's own path), rank 0 only ----
+    single_process = None
+    if world > 1:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                multi = fb.MultiGpuContext(scene, list(range(world)), precision)
+                alone, _ = r.ctx.render(seed=42, spp=spp)
+                res = {}
+                for split_name, split_id in (("tiles", fb.SPLIT_TILES), ("samples", fb.SPLIT_SAMPLES)):
+                    for _ in range(3):
+                        img, mst = multi.render(out=host_np, seed=42, spp=spp, split=split_id)
+                    t_sp = time.perf_counter()
+                    for _ in range(args.steps):
+                        img, mst = multi.render(out=host_np, seed=42, spp=spp, split=split_id)
+                    ms_sp = (time.perf_counter() - t_sp) * 1e3 / args.steps
+                    d = np.abs(alone.astype(np.float64) - img.astype(np.float64))
+                    res[split_name] = {"e2e_ms_per_frame": ms_sp, "e2e_mrays_s": mst.rays / (ms_sp * 1e-3) / 1e6, "slowest_share_kernel_ms": mst.device_ms,
+                                       "bit_identical_to_one_gpu": bool(np.array_equal(alone, img)), "max_abs_diff": float(d.max())}
+                multi.close()
+                single_process = dict(res, note="fray_gpu_multi_render: one process, a context and a host thread per GPU, shares stored into GPU 0's "
+                                                 "frame over NVLink peer access, host buffer in and out (the path of `fray --gpu --devices N`)")
+            except fb.FrayError as e:
+                single_process = {"error": str(e)}
+            store.set("fray_single_process_done", "1")
+        else:
+            store.wait(["fray_single_process_done"])  # on the CPU: an NCCL barrier would spin on this rank's GPU while rank 0 measures
+
     if rank == 0:
         fp32_peak, l2_peak = fb.measure_peaks(local_rank, 20.0)
         kernel_ms_per_launch = kernel_total_ms / args.steps
@@ -426,6 +454,8 @@ def main():
         }
         if multi_check:
             line["multi_gpu_check"] = multi_check
+        if single_process:
+            line["single_process"] = single_process
         if world == 1 and not args.no_other_configs and args.config == HEADLINE and precision == fb.FP32:
             line["other_configs"] = [quick_config(fb, name, local_rank, fp32_peak) for name in sorted(CONFIGS) if name != HEADLINE]
         if world == 1 and not args.no_cpu_baseline:

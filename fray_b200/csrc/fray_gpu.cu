@@ -584,8 +584,8 @@ int fray_gpu_frame_export(FrayGpuCtx* c, void** d_frame, unsigned char handle[64
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the IPC handle as 64 opaque bytes");
 	if (!c || !d_frame || !handle) return fail(FRAY_GPU_EINVAL, "null argument");
 	CUDA_TRY(cudaSetDevice(c->device));
-	if (!c->dShared) {
-		const size_t bytes = (size_t) c->width * c->height * 3 * sizeof(float);
+	if (!c->dShared) { // TWO frames back to back (see include/fray_gpu.h: double buffering)
+		const size_t bytes = 2 * (size_t) c->width * c->height * 3 * sizeof(float);
 		CUDA_TRY(cudaMalloc(&c->dShared, bytes));
 		CUDA_TRY(cudaMemset(c->dShared, 0, bytes));
 	}

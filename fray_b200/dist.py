@@ -14,7 +14,10 @@ static and needs exactly one collective at the end of the frame:
 * ``p2p``     -- the tile split without the reduction: rank 0 exports its frame (CUDA IPC), every rank maps it and its
                  kernels store the finished pixels of their own tiles straight into it over NVLink; a one-element
                  all-reduce on the render streams orders "everyone has written" before "rank 0 reads". No partial frames, no
-                 clearing, no 1.9 MB reduce, no resolve pass. Falls back to ``tiles`` where peer mapping is unavailable.
+                 clearing, no 1.9 MB reduce, no resolve pass. The exported allocation holds TWO frames used alternately: the
+                 peers' stores of frame k+1 go to the other one while rank 0 may still be copying frame k to the host, and they
+                 cannot start frame k+2 before the all-reduce of frame k+1, which rank 0 enters only after that copy (stream
+                 order). Falls back to ``tiles`` where peer mapping is unavailable.
 
 The scene is replicated (the largest bundled scene is ~25 MB). There is no collective inside the render path.
 """
@@ -76,7 +79,8 @@ class DistributedRenderer:
         self.ctx = fb.GpuContext(scene, self.device, precision)
         h, w = scene.height, scene.width
         self.shape = (h, w, 3)
-        self.peer_frame = 0  # p2p: address of rank 0's frame as seen from this GPU
+        self.peer_frame = 0  # p2p: address of rank 0's pair of frames as seen from this GPU
+        self.frames_rendered = 0  # p2p: frame k goes to buffer k % 2
         self.frame = None
         if self.mode == "p2p" and self.world > 1 and not self._setup_p2p():
             self.mode = "tiles"
@@ -117,7 +121,8 @@ class DistributedRenderer:
         if self.rank == 0:
             # a tensor view of the exported frame for reads on rank 0 (the memory belongs to the context)
             n = self.shape[0] * self.shape[1] * self.shape[2]
-            self.frame = self._wrap_device_pointer(self.peer_frame, n).view(self.shape)
+            self.frame_pair = self._wrap_device_pointer(self.peer_frame, 2 * n).view((2,) + self.shape)
+            self.frame = self.frame_pair[0]
         return True
 
     def _wrap_device_pointer(self, ptr: int, count: int):
@@ -134,9 +139,14 @@ class DistributedRenderer:
         # torch's default stream has handle 0, which the C ABI reads as "the context's own stream": name it explicitly
         stream = torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
         if self.mode == "p2p":
-            self.ctx.render_device(self.peer_frame, stream, spp=self.spp, seed=seed, flags=fb.FRAME_OWNED_ONLY,
+            which = self.frames_rendered & 1  # double buffering: see the module docstring
+            self.frames_rendered += 1
+            target = self.peer_frame + which * self.shape[0] * self.shape[1] * self.shape[2] * 4
+            self.ctx.render_device(target, stream, spp=self.spp, seed=seed, flags=fb.FRAME_OWNED_ONLY,
                                    bucket_rank=self.rank, bucket_count=self.world)
             self.dist.all_reduce(self.token)  # stream-ordered barrier: every rank's stores precede rank 0's reads
+            if self.rank == 0:
+                self.frame = self.frame_pair[which]
             return
         kw = shard(self.rank, self.world, self.spp, self.mode)
         self.ctx.render_device(self.partial.data_ptr(), stream, spp=self.spp, seed=seed, flags=fb.FRAME_SUM, **kw)

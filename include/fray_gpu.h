@@ -311,8 +311,10 @@ int fray_gpu_render(FrayGpuCtx* ctx, const FrayGpuFrame* frame, float* rgb_out, 
  * after fray_gpu_sync(). */
 int fray_gpu_render_device(FrayGpuCtx* ctx, const FrayGpuFrame* frame, void* d_rgb, void* cuda_stream);
 
-/* Peer-to-peer frames (multi-GPU tile split without a reduction). fray_gpu_frame_export() allocates a frame of
- * width*height*3 floats on the context's device (owned by the context) and returns its address and an opaque 64-byte handle
+/* Peer-to-peer frames (multi-GPU tile split without a reduction). fray_gpu_frame_export() allocates TWO frames of
+ * width*height*3 floats back to back on the context's device (owned by the context; the second starts width*height*3 floats
+ * after the returned address -- alternate between them from frame to frame, so that the shares of frame k+1 never land in memory
+ * the owner is still reading frame k from) and returns the address and an opaque 64-byte handle
  * (a cudaIpcMemHandle_t); another PROCESS that drives another GPU of the same node passes the handle to
  * fray_gpu_frame_import() and gets an address through which its kernels write into that frame over NVLink (pass it as d_rgb to
  * fray_gpu_render_device with FRAY_FRAME_OWNED_ONLY). The importer calls fray_gpu_frame_close() when done. The caller

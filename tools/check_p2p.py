@@ -40,6 +40,26 @@ def main():
             d = np.abs(img - want).max()
             print(f"{mode:8s} (ran as {used:7s}) max |difference| to the single-GPU frame: {d:.3e}")
             assert d <= (1e-5 if mode == "samples" else 0.0) or (mode != "samples" and d < 1e-6), (mode, d)
+    # a moving camera in p2p mode: every frame differs, rank 0 copies frame k to the host while the peers already store frame
+    # k+1 into the other half of the exported pair -- each frame must equal the single-GPU frame of the same camera
+    r = fdist.DistributedRenderer(scene, mode="p2p", device=local)
+    single = fb.GpuContext(scene, local, fb.FP32) if rank == 0 else None
+    worst = 0.0
+    for k in range(12):
+        cam = scene.move_camera(dx=0.0 if k == 0 else 3.0, dz=0.0 if k == 0 else 1.5, dyaw=0.0 if k == 0 else 2.0)  # same parse on every rank: same cameras
+        r.ctx.update_camera(cam)
+        out = r.render()
+        if rank == 0:
+            single.update_camera(cam)
+            want, _ = single.render()
+            worst = max(worst, float(np.abs(out - want).max()))
+    if rank == 0:
+        single.close()
+        print(f"p2p, 12 frames with a moving camera (ran as {r.mode}): max |difference| to the single-GPU frames: {worst:.3e}")
+        assert worst < 1e-6, worst
+    dist.barrier()
+    r.close()
+    if rank == 0:
         print(f"check_p2p: OK on {world} GPUs")
     dist.barrier()
     dist.destroy_process_group()
