@@ -132,6 +132,7 @@ def gpu_lib() -> C.CDLL:
         L.fray_gpu_render.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.POINTER(FrayStats)]
         L.fray_gpu_render_device.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.c_void_p]
         L.fray_gpu_resolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.fray_gpu_resolve_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.fray_gpu_frame_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_char_p]
         L.fray_gpu_frame_import.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
         L.fray_gpu_frame_close.argtypes = [C.c_void_p, C.c_void_p]
@@ -261,6 +262,10 @@ class GpuContext:
 
     def resolve_device(self, d_sum: int, d_rgb: int, spp: int, stream: int = 0):
         self._check(self._lib.fray_gpu_resolve_device(self._ctx, d_sum, d_rgb, spp, stream), "fray_gpu_resolve_device")
+
+    def resolve_to_host(self, d_sum: int, pinned_host: int, spp: int, stream: int = 0):
+        """sum / spp stored straight into page-locked host memory (no separate device-to-host copy)."""
+        self._check(self._lib.fray_gpu_resolve_to_host(self._ctx, d_sum, pinned_host, spp, stream), "fray_gpu_resolve_to_host")
 
     def frame_export(self) -> tuple[int, bytes]:
         """(device address, 64-byte IPC handle) of a context-owned frame other processes can map (fray_gpu_frame_export)."""

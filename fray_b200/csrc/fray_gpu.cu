@@ -616,6 +616,30 @@ int fray_gpu_frame_close(FrayGpuCtx* c, void* d_frame)
 	return FRAY_GPU_OK;
 }
 
+// device-visible address of a page-locked host buffer (nullptr if `host` is ordinary pageable memory)
+static float* mappedHostPointer(const void* host)
+{
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, host) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return (float*) attr.devicePointer;
+}
+
+int fray_gpu_resolve_to_host(FrayGpuCtx* c, const void* d_sum, float* pinned_rgb, int32_t spp, void* cuda_stream)
+{
+	if (!c || !d_sum || !pinned_rgb || spp < 1) return fail(FRAY_GPU_EINVAL, "bad argument");
+	CUDA_TRY(cudaSetDevice(c->device));
+	float* dev = mappedHostPointer(pinned_rgb);
+	if (!dev) return fail(FRAY_GPU_EINVAL, "fray_gpu_resolve_to_host needs page-locked (pinned) host memory");
+	const size_t n = (size_t) c->width * c->height * 3;
+	cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : c->stream;
+	resolveKernel<<<c->numSMs * 4, 256, 0, st>>>((const float*) d_sum, dev, n, (float) spp);
+	CUDA_TRY(cudaGetLastError());
+	return FRAY_GPU_OK;
+}
+
 int fray_gpu_resolve_device(FrayGpuCtx* c, const void* d_sum, void* d_rgb, int32_t spp, void* cuda_stream)
 {
 	if (!c || !d_sum || !d_rgb || spp < 1) return fail(FRAY_GPU_EINVAL, "bad argument");
@@ -985,15 +1009,20 @@ int fray_gpu_multi_render(FrayGpuMulti* mg, const FrayGpuFrame* frame, int split
 		cudaSetDevice(c0->device);
 		cudaError_t e = cudaSuccess;
 		for (int d = 0; d < n && e == cudaSuccess; d++) e = cudaStreamWaitEvent(c0->stream, mg->done[d], 0);
-		if (e == cudaSuccess && split == FRAY_GPU_SPLIT_SAMPLES) {
-			sumPartialsKernel<<<c0->numSMs * 4, 256, 0, c0->stream>>>(mg->dPartials, n, frameFloats, c0->dFrame, (frame->flags & FRAY_FRAME_SUM) ? 1.0f : (float) spp);
-			e = cudaGetLastError();
-		}
 		const size_t bytes = frameFloats * sizeof(float);
-		cudaPointerAttributes attr;
-		const bool pinned = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-		cudaGetLastError();
-		if (e == cudaSuccess) e = cudaMemcpyAsync(pinned ? rgb_out : c0->hStaging, c0->dFrame, bytes, cudaMemcpyDeviceToHost, c0->stream);
+		float* mapped = mappedHostPointer(rgb_out); // a page-locked caller buffer: the GPU writes it directly
+		const bool pinned = mapped != nullptr;
+		if (!mapped) mapped = mappedHostPointer(c0->hStaging);
+		bool copied = false;
+		if (e == cudaSuccess && split == FRAY_GPU_SPLIT_SAMPLES) {
+			// add the shares and hand the frame over in one pass: the sums are stored straight into host memory over PCIe
+			// (no frame on device 0, no separate device-to-host copy)
+			float* target = mapped ? mapped : c0->dFrame;
+			sumPartialsKernel<<<c0->numSMs * 4, 256, 0, c0->stream>>>(mg->dPartials, n, frameFloats, target, (frame->flags & FRAY_FRAME_SUM) ? 1.0f : (float) spp);
+			e = cudaGetLastError();
+			copied = mapped != nullptr;
+		}
+		if (e == cudaSuccess && !copied) e = cudaMemcpyAsync(pinned ? rgb_out : c0->hStaging, c0->dFrame, bytes, cudaMemcpyDeviceToHost, c0->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c0->stream);
 		if (e == cudaSuccess && !pinned) memcpy(rgb_out, c0->hStaging, bytes);
 		if (e != cudaSuccess) rc = fail(FRAY_GPU_ECUDA, std::string("assembling the frame: ") + cudaGetErrorString(e));

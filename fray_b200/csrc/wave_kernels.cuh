@@ -19,6 +19,9 @@
 // sub-queue of its own number: atomics on ONE address retire at ~3 ns each on this chip, which for 8 M pushes per frame
 // (260 k warp-level atomics) was most of the frame; spread over 64 addresses they disappear. Consumers see a dense index
 // space again through the prefix sums of the sub-queue counts (64 words, scanned once per CTA into shared memory).
+// (Measured and dropped: binning the queued rays into "touches the world box of a KD mesh" / "does not", so that a TRACE warp
+// holds only tree walkers or none. hw9/dragon, where 11 of 32 lanes are busy in the walk of the 10 M glossy rays, did not move:
+// 6.57 -> 6.60 ms. The walkers themselves diverge -- random directions off the floor, trees of very different depth along them.)
 // Persistent grids; work is handed out dynamically in groups of 32 consecutive entries, one warp-level atomicAdd per group,
 // on FRAY_WAVE_STRIPES interleaved counters for the same reason (stripe s owns the groups s, s + 16, s + 32, ...; a warp works
 // on its own stripe until that is used up, then helps the next one). Static round-robin was 25-30 % slower here: the cost of a
@@ -110,11 +113,15 @@ __device__ __forceinline__ unsigned waveRegion() { return (blockIdx.x * 4u + (th
 // threads of the CTA; `counters` = the queue's counter block, `cap` = entries per sub-queue.
 __device__ __forceinline__ void waveScanQueue(const unsigned* counters, unsigned cap, unsigned* prefix)
 {
+	static_assert(FRAY_WAVE_REGIONS <= 128, "one thread of the 128 per counter");
+	__shared__ unsigned counts[FRAY_WAVE_REGIONS];
+	if (threadIdx.x < FRAY_WAVE_REGIONS) counts[threadIdx.x] = min(counters[threadIdx.x * FRAY_WAVE_CTR_STRIDE], cap); // all loads in flight at once
+	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned sum = 0;
 		for (int r = 0; r < FRAY_WAVE_REGIONS; r++) {
 			prefix[r] = sum;
-			sum += min(counters[r * FRAY_WAVE_CTR_STRIDE], cap);
+			sum += counts[r];
 		}
 		prefix[FRAY_WAVE_REGIONS] = sum;
 	}

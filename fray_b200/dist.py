@@ -156,12 +156,25 @@ class DistributedRenderer:
             self.ctx.resolve_device(self.partial.data_ptr(), self.frame.data_ptr(), self.spp, stream)
 
     def render(self, seed: int = 42) -> np.ndarray | None:
-        """End to end: render, exchange, and bring the frame to (pinned) host memory on rank 0."""
-        self.render_device(seed)
+        """End to end: render, exchange, and bring the frame to (pinned) host memory on rank 0. With a reduction, rank 0's
+        resolve pass stores the quotients straight into the pinned frame (fray_gpu_resolve_to_host): no device-to-host copy."""
+        if self.mode == "p2p":
+            self.render_device(seed)
+            if self.rank != 0:
+                return None
+            self.host_frame.copy_(self.frame, non_blocking=True)
+            self.torch.cuda.current_stream().synchronize()
+            return self.host_frame.numpy()
+        torch = self.torch
+        stream = torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
+        kw = shard(self.rank, self.world, self.spp, self.mode)
+        self.ctx.render_device(self.partial.data_ptr(), stream, spp=self.spp, seed=seed, flags=fb.FRAME_SUM, **kw)
+        if self.world > 1:
+            self.dist.reduce(self.partial, dst=0, op=self.dist.ReduceOp.SUM)
         if self.rank != 0:
             return None
-        self.host_frame.copy_(self.frame, non_blocking=True)
-        self.torch.cuda.current_stream().synchronize()
+        self.ctx.resolve_to_host(self.partial.data_ptr(), self.host_frame.data_ptr(), self.spp, stream)
+        torch.cuda.current_stream().synchronize()
         return self.host_frame.numpy()
 
     def stats(self) -> fb.RenderStats:

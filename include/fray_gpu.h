@@ -326,6 +326,11 @@ int fray_gpu_frame_close(FrayGpuCtx* ctx, void* d_frame);
 /* d_rgb[i] = d_sum[i] / spp on the device (the `avg / samplesPerPixel` of src/main.cpp:360). */
 int fray_gpu_resolve_device(FrayGpuCtx* ctx, const void* d_sum, void* d_rgb, int32_t spp, void* cuda_stream);
 
+/* The same, but the frame goes straight to the HOST: pinned_rgb must be page-locked host memory (cudaMallocHost /
+ * cudaHostRegister, e.g. a pinned torch tensor); the kernel stores the quotients into it over PCIe, so no separate
+ * device-to-host copy follows. Asynchronous on `cuda_stream`; FRAY_GPU_EINVAL for pageable memory. */
+int fray_gpu_resolve_to_host(FrayGpuCtx* ctx, const void* d_sum, float* pinned_rgb, int32_t spp, void* cuda_stream);
+
 /* Wait for the context's outstanding work and fetch the statistics of the last render. */
 int fray_gpu_sync(FrayGpuCtx* ctx, FrayGpuStats* stats);
 

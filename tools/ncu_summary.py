@@ -2,6 +2,7 @@
 """Summarise an .ncu-rep (read here, without a GPU): headline metrics, stall reasons, opcode mix and the hot basic blocks.
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--blocks]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep --json profiles/ncu_c3.json    (the figures bench.py reports under roofline.ncu)
 """
 import collections
 import csv
@@ -27,8 +28,42 @@ def ncu(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
+def as_json(rep, out):
+    """Pipe utilisation as ncu measured it on this capture: what bench.py prints next to the algorithmic roofline fraction."""
+    import json
+    import os
+    rows = ncu(rep, 'raw')
+    hdr, units, val = rows[0], rows[1], rows[2]
+    get = lambda k: float(val[hdr.index(k)].replace(',', ''))
+    unit = lambda k: units[hdr.index(k)]
+    dur = get('gpu__time_duration.sum') * {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 'usecond': 1e-3, 'msecond': 1.0, 'nsecond': 1e-6}.get(unit('gpu__time_duration.sum'), 1e-3)
+    ffma = get('smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed')
+    fmul = get('smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed')
+    fadd = get('smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed')
+    lanes = 148 * 128  # FP32 lanes of the chip
+    def mb(k):
+        return get(k) * {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}.get(unit(k), 1e-6)
+    d = {
+        "capture": os.path.basename(rep), "kernel": val[hdr.index('Kernel Name')], "kernel_ms_under_ncu": dur,
+        "pipe_fma_cycles_active_pct": get('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'),
+        "issue_slots_busy_pct": get('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+        "executed_fp32_frac_of_peak": (2 * ffma + fmul + fadd) / (2 * lanes),
+        "ffma_thread_inst_per_cycle": ffma, "ffma_peak_per_cycle": lanes,
+        "active_threads_per_warp_inst": get('smsp__thread_inst_executed_per_inst_executed.ratio'),
+        "dram_read_mb": mb('dram__bytes_read.sum'), "dram_write_mb": mb('dram__bytes_write.sum'),
+        "registers_per_thread": get('launch__registers_per_thread'),
+        "note": "ncu --set full --clock-control none of ONE launch (cold caches, serialised); executed_fp32_frac_of_peak = "
+                "(2 FFMA + FMUL + FADD thread instructions per cycle) / (2 x 148 x 128)",
+    }
+    with open(out, 'w') as f:
+        json.dump(d, f, indent=1)
+    print(json.dumps(d, indent=1))
+
+
 def main():
     rep = sys.argv[1]
+    if '--json' in sys.argv:
+        return as_json(rep, sys.argv[sys.argv.index('--json') + 1])
     rows = ncu(rep, 'raw')
     hdr, units = rows[0], rows[1]
     for val in rows[2:]:
