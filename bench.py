@@ -425,8 +425,7 @@ def main():
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
             "frac_is": "ALGORITHMIC: rays/s x the reference algorithm's flop per ray (SURVEY.md 8d cost model), i.e. reference work per second "
                        "against the FP32 peak -- not the share of the pipe these kernels keep busy (see `ncu` for that)",
-            # no DRAM figure is pasted here: the scene (< 1 MB) and the frame live in L2, see profiles/ for the ncu capture of this build
-            "traffic": None,
+            "traffic": None,  # filled below from the ncu capture in profiles/ when there is one for this configuration
             "peak_source": "FFMA micro-benchmark run in this process (fray_gpu_measure_peaks); MEASURED_PEAKS.json holds no FP32 figure",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
             "kernel": cfg["kernel"] if precision == fb.FP32 else "renderKernel<double, ...> (parity precision)",
@@ -441,6 +440,9 @@ def main():
         if os.path.exists(ncu_file) and precision == fb.FP32:
             with open(ncu_file) as fp:
                 roofline["ncu"] = json.load(fp)
+            if world == 1:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch in that capture (profiles/, same build)
+                roofline["traffic"] = int((roofline["ncu"]["dram_read_mb"] + roofline["ncu"]["dram_write_mb"]) * 1e6)
+                roofline["traffic_source"] = f"profiles/{os.path.basename(ncu_file)}: ncu --set full capture of this kernel on this workload"
         line = {
             "metric": metric_name(cfg, W, H), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
