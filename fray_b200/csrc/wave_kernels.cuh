@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(128, 8) waveTraceKernel(const DScene<float> sc
 
 // ---- SHADE -----------------------------------------------------------------------------------------------------------------
 template <int F>
-__global__ void __launch_bounds__(128, 4) waveShadeKernel(const DScene<float> sc, const WaveParams p)
+__global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc, const WaveParams p)
 {
 	const FlatTab ft = stageFlat<float, F>(sc);
 	__shared__ unsigned prefix[FRAY_WAVE_REGIONS + 1];
