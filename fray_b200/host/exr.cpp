@@ -376,6 +376,266 @@ bool pizDecode(const uint8_t* in, size_t nIn, std::vector<uint8_t>& raw, const s
 	return true;
 }
 
+// ---- PIZ: encoder ------------------------------------------------------------------------------------
+// The inverse of the decoder above, as Imf::RgbaOutputFile applies it by default (the reference's Bitmap::saveEXR,
+// /root/reference/src/bitmap.cpp:266-284, leaves the header's compression at its default, PIZ): per chunk of 32 scan lines
+// the HALF samples are gathered channel by channel, mapped through the table of values that occur (bitmap + LUT), transformed
+// by the 2-D Haar-like wavelet and Huffman-coded with a run-length symbol.
+
+struct BitWriter {
+	std::vector<uint8_t>& out;
+	uint64_t c = 0;
+	int lc = 0;
+	void put(int nBits, uint64_t bits)
+	{
+		c = (c << nBits) | bits;
+		lc += nBits;
+		while (lc >= 8) {
+			lc -= 8;
+			out.push_back((uint8_t) (c >> lc));
+		}
+	}
+	void flush()
+	{
+		if (lc > 0) out.push_back((uint8_t) (c << (8 - lc)));
+		lc = 0;
+		c = 0;
+	}
+};
+
+// code lengths of a Huffman code for `freq` (symbols im..iM with non-zero frequency), as code[i] = length; then the canonical
+// codes the decoder derives from the lengths (hufUnpackTable): code[i] = length | (value << 6)
+bool hufBuildEncTable(const std::vector<uint64_t>& freq, int im, int iM, std::vector<uint64_t>& code)
+{
+	struct Node { uint64_t f; int left, right; };
+	std::vector<Node> nodes;
+	std::vector<int> leafOf(HUF_ENCSIZE, -1);
+	typedef std::pair<uint64_t, int> Item; // (frequency, node): ties by node number, so the table is deterministic
+	std::vector<Item> heap;
+	for (int i = im; i <= iM; i++)
+		if (freq[i]) {
+			leafOf[i] = (int) nodes.size();
+			heap.push_back(Item(freq[i], (int) nodes.size()));
+			nodes.push_back(Node{ freq[i], -1, -1 });
+		}
+	if (heap.empty()) return false;
+	std::fill(code.begin(), code.end(), 0);
+	if (heap.size() == 1) {
+		for (int i = im; i <= iM; i++)
+			if (leafOf[i] >= 0) code[i] = 1;
+	} else {
+		auto cmp = [](const Item& a, const Item& b) { return a > b; };
+		std::make_heap(heap.begin(), heap.end(), cmp);
+		while (heap.size() > 1) {
+			std::pop_heap(heap.begin(), heap.end(), cmp);
+			const Item a = heap.back();
+			heap.pop_back();
+			std::pop_heap(heap.begin(), heap.end(), cmp);
+			const Item b = heap.back();
+			heap.pop_back();
+			nodes.push_back(Node{ a.first + b.first, a.second, b.second });
+			heap.push_back(Item(a.first + b.first, (int) nodes.size() - 1));
+			std::push_heap(heap.begin(), heap.end(), cmp);
+		}
+		// depth of every leaf
+		std::vector<int> depth(nodes.size(), 0);
+		for (int n = (int) nodes.size() - 1; n >= 0; n--)
+			if (nodes[n].left >= 0) {
+				depth[nodes[n].left] = depth[n] + 1;
+				depth[nodes[n].right] = depth[n] + 1;
+			}
+		for (int i = im; i <= iM; i++)
+			if (leafOf[i] >= 0) {
+				if (depth[leafOf[i]] > 58) return false; // the format stores lengths in 6 bits, 59..63 are run codes
+				code[i] = (uint64_t) depth[leafOf[i]];
+			}
+	}
+	uint64_t n[59] = { 0 };
+	for (int i = 0; i < HUF_ENCSIZE; i++) n[code[i]]++;
+	uint64_t c = 0;
+	for (int i = 58; i > 0; i--) {
+		const uint64_t nc = (c + n[i]) >> 1;
+		n[i] = c;
+		c = nc;
+	}
+	for (int i = 0; i < HUF_ENCSIZE; i++) {
+		const int l = (int) code[i];
+		if (l > 0) code[i] = l | (n[l]++ << 6);
+	}
+	return true;
+}
+
+void hufPackTable(const std::vector<uint64_t>& code, int im, int iM, BitWriter& bw)
+{
+	for (; im <= iM; im++) {
+		const int l = (int) (code[im] & 63);
+		if (l == 0) {
+			int run = 1;
+			while (im + run <= iM && run < 261 && (code[im + run] & 63) == 0) run++;
+			if (run >= 2) {
+				if (run >= 6) {
+					bw.put(6, 63);
+					bw.put(8, (uint64_t) (run - 6));
+				} else {
+					bw.put(6, (uint64_t) (59 + run - 2));
+				}
+				im += run - 1;
+				continue;
+			}
+		}
+		bw.put(6, (uint64_t) l);
+	}
+	bw.flush();
+}
+
+// Huffman-compress n 16-bit words: header {im, iM, table bytes, data bits, 0}, packed code lengths, code stream
+void hufCompress(const uint16_t* raw, size_t n, std::vector<uint8_t>& out)
+{
+	out.clear();
+	if (n == 0) return;
+	std::vector<uint64_t> freq(HUF_ENCSIZE, 0);
+	for (size_t i = 0; i < n; i++) freq[raw[i]]++;
+	int im = 0, iM = HUF_ENCSIZE - 2;
+	while (!freq[im]) im++;
+	while (!freq[iM]) iM--;
+	iM++; // the run-length symbol: one past the largest value in use, frequency 1
+	freq[iM] = 1;
+	std::vector<uint64_t> code(HUF_ENCSIZE, 0);
+	hufBuildEncTable(freq, im, iM, code);
+	out.resize(20, 0);
+	BitWriter table{ out };
+	hufPackTable(code, im, iM, table);
+	const uint32_t tableBytes = (uint32_t) (out.size() - 20);
+	const size_t dataStart = out.size();
+	BitWriter bw{ out };
+	auto putCode = [&](uint64_t cde) { bw.put((int) (cde & 63), cde >> 6); };
+	const uint64_t runCode = code[iM];
+	auto send = [&](uint64_t sCode, int runCount) {
+		const int ls = (int) (sCode & 63), lr = (int) (runCode & 63);
+		if (ls + lr + 8 < ls * runCount) {
+			putCode(sCode);
+			putCode(runCode);
+			bw.put(8, (uint64_t) runCount);
+		} else {
+			while (runCount-- >= 0) putCode(sCode);
+		}
+	};
+	uint16_t sym = raw[0];
+	int run = 0;
+	for (size_t i = 1; i < n; i++) {
+		if (raw[i] == sym && run < 255) {
+			run++;
+		} else {
+			send(code[sym], run);
+			run = 0;
+		}
+		sym = raw[i];
+	}
+	send(code[sym], run);
+	const uint32_t nBits = (uint32_t) ((out.size() - dataStart) * 8 + (size_t) bw.lc);
+	bw.flush();
+	const uint32_t hdr[5] = { (uint32_t) im, (uint32_t) iM, tableBytes, nBits, 0 };
+	memcpy(out.data(), hdr, 20);
+}
+
+inline void wenc14(uint16_t a, uint16_t b, uint16_t& l, uint16_t& h)
+{
+	const int as = (int16_t) a, bs = (int16_t) b;
+	l = (uint16_t) (int16_t) ((as + bs) >> 1);
+	h = (uint16_t) (int16_t) (as - bs);
+}
+
+inline void wenc16(uint16_t a, uint16_t b, uint16_t& l, uint16_t& h)
+{
+	const int ao = (a + 0x8000) & 0xffff;
+	int m = (ao + b) >> 1;
+	int d = ao - b;
+	if (d < 0) m = (m + 0x8000) & 0xffff;
+	d &= 0xffff;
+	l = (uint16_t) m;
+	h = (uint16_t) d;
+}
+
+void wav2Encode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx)
+{
+	const bool w14 = mx < (1 << 14);
+	const int n = nx > ny ? ny : nx;
+	int p = 1, p2 = 2;
+	auto enc = [&](uint16_t a, uint16_t b, uint16_t& l, uint16_t& h) { if (w14) wenc14(a, b, l, h); else wenc16(a, b, l, h); };
+	while (p2 <= n) {
+		uint16_t* py = in;
+		uint16_t* ey = in + (ptrdiff_t) oy * (ny - p2);
+		const int oy1 = oy * p, oy2 = oy * p2, ox1 = ox * p, ox2 = ox * p2;
+		uint16_t i00, i01, i10, i11;
+		for (; py <= ey; py += oy2) {
+			uint16_t* px = py;
+			uint16_t* ex = py + (ptrdiff_t) ox * (nx - p2);
+			for (; px <= ex; px += ox2) {
+				uint16_t* p01 = px + ox1;
+				uint16_t* p10 = px + oy1;
+				uint16_t* p11 = p10 + ox1;
+				enc(*px, *p01, i00, i01);
+				enc(*p10, *p11, i10, i11);
+				enc(i00, i10, *px, *p10);
+				enc(i01, i11, *p01, *p11);
+			}
+			if (nx & p) { // odd column
+				uint16_t* p10 = px + oy1;
+				enc(*px, *p10, i00, *p10);
+				*px = i00;
+			}
+		}
+		if (ny & p) { // odd line
+			uint16_t* px = py;
+			uint16_t* ex = py + (ptrdiff_t) ox * (nx - p2);
+			for (; px <= ex; px += ox2) {
+				uint16_t* p01 = px + ox1;
+				enc(*px, *p01, i00, *p01);
+				*px = i00;
+			}
+		}
+		p = p2;
+		p2 <<= 1;
+	}
+}
+
+// `raw`: `lines` scan lines of `numChans` HALF channels, channel by channel within a line -> one PIZ chunk
+void pizEncode(const uint16_t* raw, int width, int lines, int numChans, std::vector<uint8_t>& out)
+{
+	const size_t plane = (size_t) width * lines, total = plane * numChans;
+	std::vector<uint16_t> tmp(total);
+	for (int y = 0; y < lines; y++)
+		for (int c = 0; c < numChans; c++)
+			memcpy(&tmp[(size_t) c * plane + (size_t) y * width], raw + ((size_t) y * numChans + c) * width, (size_t) width * 2);
+	const int BITMAP_SIZE = 8192;
+	std::vector<uint8_t> bitmap(BITMAP_SIZE, 0);
+	for (uint16_t v: tmp) bitmap[v >> 3] |= (uint8_t) (1 << (v & 7));
+	bitmap[0] &= ~1; // zero is always in the table, never in the bitmap
+	int minNZ = BITMAP_SIZE - 1, maxNZ = 0;
+	for (int i = 0; i < BITMAP_SIZE; i++)
+		if (bitmap[i]) {
+			if (minNZ > i) minNZ = i;
+			if (maxNZ < i) maxNZ = i;
+		}
+	std::vector<uint16_t> lut(65536, 0);
+	int k = 0;
+	for (int i = 0; i < 65536; i++)
+		if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[i] = (uint16_t) k++;
+	const uint16_t maxValue = (uint16_t) (k - 1);
+	for (uint16_t& v: tmp) v = lut[v];
+	for (int c = 0; c < numChans; c++) wav2Encode(tmp.data() + (size_t) c * plane, width, 1, lines, width, maxValue);
+	std::vector<uint8_t> huf;
+	hufCompress(tmp.data(), total, huf);
+	out.clear();
+	const uint16_t mn = (uint16_t) minNZ, mx = (uint16_t) maxNZ;
+	out.insert(out.end(), (const uint8_t*) &mn, (const uint8_t*) &mn + 2);
+	out.insert(out.end(), (const uint8_t*) &mx, (const uint8_t*) &mx + 2);
+	if (minNZ <= maxNZ) out.insert(out.end(), bitmap.begin() + minNZ, bitmap.begin() + maxNZ + 1);
+	const int32_t length = (int32_t) huf.size();
+	out.insert(out.end(), (const uint8_t*) &length, (const uint8_t*) &length + 4);
+	out.insert(out.end(), huf.begin(), huf.end());
+}
+
 // ---- ZIP -------------------------------------------------------------------------------------------
 
 bool zipDecode(const uint8_t* in, size_t nIn, std::vector<uint8_t>& raw, size_t expected)
@@ -565,7 +825,7 @@ bool Bitmap::saveEXR(const char* filename) const
 	}
 	hdr.push_back(0);
 	attr("compression", "compression", 1);
-	hdr.push_back(0);
+	hdr.push_back(4); // PIZ_COMPRESSION: what Imf::RgbaOutputFile writes by default (src/bitmap.cpp:266-284)
 	attr("dataWindow", "box2i", 16);
 	putI(0); putI(0); putI(width - 1); putI(height - 1);
 	attr("displayWindow", "box2i", 16);
@@ -579,23 +839,38 @@ bool Bitmap::saveEXR(const char* filename) const
 	attr("screenWindowWidth", "float", 4);
 	putF(1.0f);
 	hdr.push_back(0);
-	const size_t lineBytes = (size_t) width * 8, chunk = 8 + lineBytes;
-	uint64_t off = hdr.size() + (uint64_t) height * 8;
-	fwrite(hdr.data(), 1, hdr.size(), fp);
-	for (int y = 0; y < height; y++, off += chunk) fwrite(&off, 8, 1, fp);
-	std::vector<uint16_t> line((size_t) width * 4);
+	// chunks of 32 scan lines, each PIZ-compressed (stored raw where that does not make it smaller, as the library does)
+	const int linesPerChunk = 32, numChunks = (height + linesPerChunk - 1) / linesPerChunk;
 	const uint16_t one = floatToHalf(1.0f);
-	for (int y = 0; y < height; y++) {
-		int32_t head[2] = { y, (int32_t) lineBytes };
-		fwrite(head, 4, 2, fp);
-		for (int x = 0; x < width; x++) {
-			const Color& c = data[(size_t) y * width + x];
-			line[x] = one;
-			line[width + x] = floatToHalf(c.b);
-			line[2 * (size_t) width + x] = floatToHalf(c.g);
-			line[3 * (size_t) width + x] = floatToHalf(c.r);
+	std::vector<std::vector<uint8_t>> chunks(numChunks);
+	std::vector<uint16_t> rawLines;
+	for (int b = 0; b < numChunks; b++) {
+		const int y0 = b * linesPerChunk, lines = std::min(linesPerChunk, height - y0);
+		rawLines.assign((size_t) width * 4 * lines, 0);
+		for (int ly = 0; ly < lines; ly++) {
+			uint16_t* line = &rawLines[(size_t) ly * width * 4];
+			for (int x = 0; x < width; x++) {
+				const Color& c = data[(size_t) (y0 + ly) * width + x];
+				line[x] = one; // A, B, G, R: channels in alphabetical order
+				line[width + x] = floatToHalf(c.b);
+				line[2 * (size_t) width + x] = floatToHalf(c.g);
+				line[3 * (size_t) width + x] = floatToHalf(c.r);
+			}
 		}
-		fwrite(line.data(), 2, line.size(), fp);
+		const size_t rawBytes = rawLines.size() * 2;
+		pizEncode(rawLines.data(), width, lines, 4, chunks[b]);
+		if (chunks[b].size() >= rawBytes) chunks[b].assign((const uint8_t*) rawLines.data(), (const uint8_t*) rawLines.data() + rawBytes);
+	}
+	uint64_t off = hdr.size() + (uint64_t) numChunks * 8;
+	fwrite(hdr.data(), 1, hdr.size(), fp);
+	for (int b = 0; b < numChunks; b++) {
+		fwrite(&off, 8, 1, fp);
+		off += 8 + chunks[b].size();
+	}
+	for (int b = 0; b < numChunks; b++) {
+		int32_t head[2] = { b * linesPerChunk, (int32_t) chunks[b].size() };
+		fwrite(head, 4, 2, fp);
+		fwrite(chunks[b].data(), 1, chunks[b].size(), fp);
 	}
 	fclose(fp);
 	return true;

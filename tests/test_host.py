@@ -191,3 +191,35 @@ def test_cli_exit_codes_follow_the_reference(tmp_path, data_dir):
     if fb.gpu_lib().fray_gpu_device_count() == 0:
         r = subprocess.run([exe, "--gpu", scene], capture_output=True, text=True)
         assert r.returncode == 252 and "no CPU fallback" in r.stderr
+
+
+def test_exr_writer_is_piz_and_openexr_reads_it(tmp_path):
+    """The writer emits what Imf::RgbaOutputFile writes by default (/root/reference/src/bitmap.cpp:266-284): HALF A,B,G,R,
+    PIZ-compressed chunks of 32 scan lines. Decoded here by OUR reader and by OpenCV's bundled OpenEXR library; sizes that
+    exercise odd widths / heights of the wavelet, a partial last chunk, flat regions (run-length symbol) and the 16-bit wavelet
+    mode (more than 2^14 distinct values)."""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(7)
+    for h, w, scale in ((70, 90, 4.0), (33, 17, 1.0), (1, 1, 1.0), (64, 64, 1e4), (150, 333, 60000.0)):
+        rgb = (rs.rand(h, w, 3) * scale).astype(np.float32)
+        rgb[: h // 2] = 0.25
+        rgb[0, 0] = [0.0, 1e-3, 1000.0]
+        p = str(tmp_path / f"piz_{h}x{w}.exr")
+        fb.save_image(p, rgb)
+        want = rgb.astype(np.float16).astype(np.float32)
+        with open(p, "rb") as f:
+            head = f.read(400)
+        i = head.index(b"compression\0compression\0")
+        assert head[i + 28] == 4  # PIZ_COMPRESSION
+        assert np.array_equal(fb.load_image(p), want)
+        other = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        if other is None:
+            pytest.skip("this OpenCV build has no OpenEXR codec")
+        assert other.shape == (h, w, 4) and np.all(other[..., 3] == 1)
+        assert np.array_equal(other[..., :3][..., ::-1], want)
+    yy, xx = np.mgrid[0:256, 0:256].astype(np.float32)
+    smooth = np.stack([xx / 256, yy / 256, (xx + yy) / 512], -1).astype(np.float32)
+    p = str(tmp_path / "smooth.exr")
+    fb.save_image(p, smooth)
+    assert os.path.getsize(p) < 256 * 256 * 8 // 4  # it does compress
