@@ -1783,10 +1783,10 @@ template <typename R, int F, typename RNG> FRAY_HD bool pathSegment(const DScene
 	};
 	const bool lambert = sType == FRAY_SHADER_LAMBERT;
 
-	// all draws of the segment: 4 skipped + 4 for the light sample + 4 for the new direction (Lambert), 4 otherwise
-	rng.ensure(lambert ? 12 : 4);
-	// the first, discarded spawnRay (src/main.cpp:219-224) only advances the stream (4 draws for Lambert)
-	if (lambert) rng.skip(4);
+	// all draws of the segment: 2 skipped + 4 for the light sample + 2 for the new direction (Lambert): two Philox blocks; 4 otherwise
+	rng.ensure(lambert ? 8 : 4);
+	// the first, discarded spawnRay (src/main.cpp:219-224) only advances the stream (its two randdouble() draws for Lambert)
+	if (lambert) rng.skip(2);
 
 	// explicitLightSample(), src/main.cpp:118-169
 	if constexpr (!Num<R>::kExact) {

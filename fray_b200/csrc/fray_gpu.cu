@@ -689,11 +689,10 @@ __global__ void rngProbeKernel(const RngProbeParams p)
 	}
 	rng.ensure(2);
 	for (int k = 0; k < 2 && i < p.n; k++) put(rng.next());
-	while (i + 12 <= p.n) {
-		rng.ensure(12);
-		rng.skip(4); i += 4;
-		for (int k = 0; k < 4; k++) put(rng.next());
-		for (int k = 0; k < 2; k++) { rng.skip(1); i++; put(rng.next()); }
+	while (i + 8 <= p.n) {
+		rng.ensure(8);
+		rng.skip(2); i += 2;
+		for (int k = 0; k < 6; k++) put(rng.next());
 	}
 }
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 		if (!active && hasItem && cur < end) { // start sample `cur`
 			const int s = cur++;
 			rng.init(p.seed, (uint32_t) (py * p.width + px), (uint32_t) s, 0);
-			rng.ensure((F & FRAY_F_LENS) ? 10 : 2); // pixel offset, two thin-lens samples per eye
+			rng.ensure((F & FRAY_F_LENS) ? 6 : 2); // pixel offset (2 draws), one thin-lens sample (2 draws) per eye
 			float ox, oy;
 			sampleOffset(randomOffsets, s, rng, ox, oy);
 			const R fx = (R) ((float) px + ox), fy = (R) ((float) py + oy);

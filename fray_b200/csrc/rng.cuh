@@ -140,18 +140,10 @@ template <int MODE> struct RngT {
 		count = target;
 	}
 	FRAY_HD float randfloat() { return (float) (next() >> 8) * (1.0f / 16777216.0f); }
-	FRAY_HD double randdouble()
-	{
-		const uint64_t lo = next();
-		const uint64_t hi = next();
-		return (double) (((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
-	}
-	// single-precision view of randdouble(): consumes the same two draws
-	FRAY_HD float randdoubleAsFloat()
-	{
-		next();
-		return (float) (next() >> 8) * (1.0f / 16777216.0f);
-	}
+	// ONE draw per double (32 random bits), see DESIGN.md "RNG contract"
+	FRAY_HD double randdouble() { return (double) next() * (1.0 / 4294967296.0); }
+	// single-precision view of randdouble(): the same draw, its top 24 bits
+	FRAY_HD float randdoubleAsFloat() { return (float) (next() >> 8) * (1.0f / 16777216.0f); }
 	FRAY_HD int randint(int a, int b)
 	{
 		const uint32_t n = (uint32_t) (b - a + 1);
@@ -161,10 +153,10 @@ template <int MODE> struct RngT {
 
 #if defined(__CUDACC__)
 // The same streams for the path-tracing kernels, generated a few blocks ahead into a per-thread ring of 16 words in shared
-// memory (layout [word][thread]: conflict-free whatever position each lane is at). A path segment consumes up to 12 draws
+// memory (layout [word][thread]: conflict-free whatever position each lane is at). A path segment consumes up to 8 draws
 // (src/main.cpp:118-169, 219-236), always at data-dependent positions of the stream; with the blocks in registers every
 // draw paid for a refill test and a four-way select (a tenth of the kernel's instructions). Here ensure(n) runs the ten
-// rounds in ONE loop per call site (three trips for a Lambert segment) and a draw is an address computation and an LDS.
+// rounds in ONE loop per call site (two trips for a Lambert segment) and a draw is an address computation and an LDS.
 // Word p of the stream lives in ring[p & 15]; generating block g overwrites block g - 4, so ensure(n) requires n <= 12.
 #define FRAY_RNG_RING_WORDS 16
 struct RngRing {
@@ -203,17 +195,8 @@ struct RngRing {
 	}
 	__device__ __forceinline__ void skip(uint32_t n) { count += n; }
 	__device__ __forceinline__ float randfloat() { return (float) (next() >> 8) * (1.0f / 16777216.0f); }
-	__device__ __forceinline__ double randdouble()
-	{
-		const uint64_t lo = next();
-		const uint64_t hi = next();
-		return (double) (((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
-	}
-	__device__ __forceinline__ float randdoubleAsFloat()
-	{
-		count++;
-		return (float) (next() >> 8) * (1.0f / 16777216.0f);
-	}
+	__device__ __forceinline__ double randdouble() { return (double) next() * (1.0 / 4294967296.0); }
+	__device__ __forceinline__ float randdoubleAsFloat() { return (float) (next() >> 8) * (1.0f / 16777216.0f); }
 	__device__ __forceinline__ int randint(int a, int b)
 	{
 		const uint32_t n = (uint32_t) (b - a + 1);

@@ -371,8 +371,8 @@ int fray_gpu_measure_peaks(int device, double ms, double* fp32_tflops, double* l
  * contract, draw for draw). Runs stream (seed, pixel, sample, branch) on `device` in one of the device forms:
  *   mode 0  on-demand blocks with round keys from the kernel parameters (the Whitted kernels),
  *   mode 1  the shared-memory ring of the path-tracing kernels, drawn sequentially in groups of up to 12,
- *   mode 2  the ring under the path tracer's own pattern: 2 draws for the pixel offset, then per path segment 4 draws
- *           skipped, 4 drawn, and twice "one skipped, one drawn" (explicitLightSample / hemisphereSample, src/main.cpp:92-169).
+ *   mode 2  the ring under the path tracer's own pattern: 2 draws for the pixel offset, then per path segment 2 draws
+ *           skipped and 6 drawn (the discarded first spawnRay, explicitLightSample, hemisphereSample; src/main.cpp:92-169, 219-236).
  * out[i] receives draw i of the stream and drawn[i] = 1 for every position i < n that was drawn (all of them in modes 0, 1). */
 int fray_gpu_rng_probe(int device, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t branch, int mode, int n, uint32_t* out, unsigned char* drawn);
 

@@ -67,6 +67,6 @@ def test_device_streams_equal_the_contract(mode):
         got = drawn.astype(bool)
         if mode < 2:
             assert got.all()
-        else:  # 2 draws, then 6 of every 12
-            assert got.sum() == min(n, 2) + 6 * ((n - 2) // 12 if n >= 2 else 0)
+        else:  # 2 draws, then 6 of every 8
+            assert got.sum() == min(n, 2) + 6 * ((n - 2) // 8 if n >= 2 else 0)
         assert np.array_equal(out[got], want[got])
