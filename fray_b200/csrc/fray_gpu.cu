@@ -389,12 +389,14 @@ static int renderWave(FrayGpuCtx* c, const RenderParams& rp, float* dOut, cudaSt
 	// the right eye of a stereo pair is queued by the left eye's SHADE (it continues the left eye's random stream): one more wave
 	c->waveCfg.waves = std::min(FRAY_WAVE_MAX, (c->waveSecondary ? c->sc32.maxTraceDepth + 1 : 1) + (stereo ? 1 : 0));
 	if (c->waveCfg.waves < 1) c->waveCfg.waves = 1;
+	// one wave and one sample per pixel: every pixel has a single owner in each pass, no accumulators (wave_kernels.cuh)
+	w.direct = (c->waveCfg.waves == 1 && w.numSamples == 1 && !getenv("FRAY_GPU_WAVE_ACCUMULATE")) ? 1 : 0;
 	CUDA_TRY(cudaMemsetAsync(c->dWaveCtr, 0, FRAY_WCTR_COUNT * sizeof(unsigned), stream));
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStart, stream));
-	CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t) c->width * c->height * 3 * sizeof(long long), stream));
+	if (!w.direct) CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t) c->width * c->height * 3 * sizeof(long long), stream));
 	cudaError_t e = launchWaveFrame(c->sc32, w, c->features, c->waveCfg);
 	if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("wavefront kernel launch: ") + cudaGetErrorString(e));
-	c->launches = c->waveCfg.waves * (c->sc32.numLights > 0 ? 3 : 2) + 1;
+	c->launches = c->waveCfg.waves * (c->sc32.numLights > 0 ? 3 : 2) + (w.direct ? 0 : 1);
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStop, stream));
 	c->pendingStats = timed;
 	c->lastStream = stream;

@@ -60,6 +60,7 @@ struct WaveParams {
 	uint2* rayC;
 	float4* hitA;        // [max(numPrimary, rayCap)]
 	int2* hitB;
+	int direct;          // single-owner frame (one wave, one sample per pixel): no accumulators, see waveAccumulate
 	int litPerRay;       // lit-record slots per ray
 	float4* litA;        // [litCap] {ip, pixel}; pixel < 0: unused slot
 	float4* litB;        // {n, meta}
@@ -141,6 +142,22 @@ __device__ __forceinline__ unsigned waveSlot(const unsigned* prefix, unsigned ca
 // meta word of rays and lit records: origin node + 1 (16 bits) | depth (8 bits) | eye (2 bits) | Phong flag
 __device__ __forceinline__ unsigned waveMeta(int origin, int depth, int eye, int phong) { return (unsigned) (origin + 1) | ((unsigned) depth << 16) | ((unsigned) eye << 24) | ((unsigned) phong << 26); }
 
+// A frame with ONE wave (no shader reflects or refracts, no stereo) and ONE sample per pixel has one owner per pixel in each
+// pass: SHADE stores what it knows (`waveStoreDirect`), SHADOW adds the light loops of the same ray (`waveAddDirect`, a plain
+// read-modify-write). That saves the accumulator clear (200 MB at 3840x2160), the resolve pass and ~6 64-bit atomics per pixel.
+__device__ __forceinline__ void waveStoreDirect(const WaveParams& p, int pixel, const Col& c)
+{
+	const float scale = p.rp.sumOnly ? 1.0f : 1.0f / (float) p.rp.spp;
+	float* o = p.rp.out + 3 * (size_t) pixel;
+	o[0] = c.r * scale; o[1] = c.g * scale; o[2] = c.b * scale;
+}
+__device__ __forceinline__ void waveAddDirect(const WaveParams& p, int pixel, const Col& c)
+{
+	const float scale = p.rp.sumOnly ? 1.0f : 1.0f / (float) p.rp.spp;
+	float* o = p.rp.out + 3 * (size_t) pixel;
+	o[0] += c.r * scale; o[1] += c.g * scale; o[2] += c.b * scale;
+}
+
 __device__ __forceinline__ void waveAccumulate(const WaveParams& p, int pixel, const Col& c)
 {
 	unsigned long long* a = reinterpret_cast<unsigned long long*>(p.acc) + 3 * (size_t) pixel;
@@ -154,7 +171,16 @@ struct WaveSink {
 	const WaveParams& p;
 	unsigned litBase; // first lit-record slot of the ray being shaded
 	int litUsed;
-	__device__ __forceinline__ void add(const WaveRay& r, const Col& c) { waveAccumulate(p, r.pixel, waveEyeColor(sc, r.eye, c)); }
+	Col known;        // direct frames: what SHADE knows of the ray's radiance, stored once by flush()
+	__device__ __forceinline__ void add(const WaveRay& r, const Col& c)
+	{
+		if (p.direct) known = known + c;
+		else waveAccumulate(p, r.pixel, waveEyeColor(sc, r.eye, c));
+	}
+	__device__ __forceinline__ void flush(int pixel)
+	{
+		if (p.direct) waveStoreDirect(p, pixel, known);
+	}
 	__device__ __forceinline__ void ray(const WaveRay& c)
 	{
 		const unsigned region = waveRegion(), cap = p.rayCap / FRAY_WAVE_REGIONS;
@@ -180,7 +206,7 @@ struct WaveSink {
 		}
 	}
 	// start the lit-record slots of ray i / close them (mark what was not used)
-	__device__ __forceinline__ void begin(unsigned i) { litBase = i * (unsigned) p.litPerRay; litUsed = 0; }
+	__device__ __forceinline__ void begin(unsigned i) { litBase = i * (unsigned) p.litPerRay; litUsed = 0; known = Col(0, 0, 0); }
 	__device__ __forceinline__ void end()
 	{
 		for (int k = litUsed; k < p.litPerRay; k++) p.litA[litBase + (unsigned) k] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
@@ -309,7 +335,7 @@ __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc
 	__shared__ unsigned prefix[FRAY_WAVE_REGIONS + 1];
 	const unsigned n = waveRayCount(p, prefix);
 	const bool randomOffsets = sc.cam.dof || sc.gi;
-	WaveSink sink{ sc, p, 0u, 0 };
+	WaveSink sink{ sc, p, 0u, 0, Col(0, 0, 0) };
 	unsigned primaries = 0;
 	WaveWork work;
 	work.init(p, 1, n);
@@ -334,6 +360,7 @@ __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc
 		uint32_t count = r.count;
 		waveShade<F>(sc, ft, r, wh, p.rp.roundKeys, p.rp.seed, count, sink);
 		sink.end();
+		sink.flush(r.pixel);
 		if (p.wave == 0 && stereo) { // the right eye goes on in the stream where the left eye's light loops stopped
 			right.count = count;
 			sink.ray(right);
@@ -355,43 +382,49 @@ __global__ void __launch_bounds__(128, CTAS) waveShadowKernel(const DScene<float
 	const FlatTab ft = stageFlat<float, F>(sc);
 	KdStackShared stk = waveStack(p);
 	__shared__ unsigned prefix[FRAY_WAVE_REGIONS + 1];
-	const unsigned long long n = (unsigned long long) waveRayCount(p, prefix) * (unsigned) p.litPerRay; // slots: litPerRay per ray of the wave
+	const unsigned n = waveRayCount(p, prefix); // one thread per ray of the wave: the light loops of all its lit records
 	const unsigned lane = threadIdx.x & 31u;
 	unsigned traced = 0;
 	WaveWork work;
 	work.init(p, 2, n);
 	for (unsigned long long group; work.next(group);) {
-		const unsigned long long rec = group * 32ull + lane;
-		if (rec >= n) continue;
-		const size_t slot = (size_t) rec;
-		const float4 a = p.litA[slot];
-		if (__float_as_int(a.w) < 0) continue; // unused slot
-		const float4 nb = p.litB[slot], dc = p.litC[slot];
-		const uint2 cs = p.litD[slot];
-		const unsigned meta = __float_as_uint(nb.w);
-		WaveLit L;
-		L.ip = V3<float>(a.x, a.y, a.z);
-		L.n = V3<float>(nb.x, nb.y, nb.z);
-		L.diffuse = Col(dc.x, dc.y, dc.z);
-		L.phong = (int) ((meta >> 26) & 1u);
-		L.pixel = __float_as_int(a.w);
-		L.sample = (int) cs.y;
-		L.origin = (int) (meta & 0xffffu) - 1;
-		L.eye = (int) ((meta >> 24) & 3u);
-		L.branch = __float_as_uint(dc.w);
-		L.count = cs.x;
-		if (L.phong) {
-			const float4 sp = p.litE[slot], rd = p.litF[slot];
-			L.specular = Col(sp.x, sp.y, sp.z);
-			L.exponent = sp.w;
-			L.rayDir = V3<float>(rd.x, rd.y, rd.z);
-		} else {
-			L.specular = Col(0, 0, 0);
-			L.exponent = 1;
-			L.rayDir = V3<float>(0, 0, 1);
+		const unsigned ray = (unsigned) group * 32u + lane;
+		if (ray >= n) continue;
+		Col sum(0, 0, 0);
+		int pixel = -1;
+		for (int k = 0; k < p.litPerRay; k++) {
+			const size_t slot = (size_t) ray * (unsigned) p.litPerRay + (unsigned) k;
+			const float4 a = p.litA[slot];
+			if (__float_as_int(a.w) < 0) break; // unused slot: a ray fills its slots from the front
+			const float4 nb = p.litB[slot], dc = p.litC[slot];
+			const uint2 cs = p.litD[slot];
+			const unsigned meta = __float_as_uint(nb.w);
+			WaveLit L;
+			L.ip = V3<float>(a.x, a.y, a.z);
+			L.n = V3<float>(nb.x, nb.y, nb.z);
+			L.diffuse = Col(dc.x, dc.y, dc.z);
+			L.phong = (int) ((meta >> 26) & 1u);
+			L.pixel = pixel = __float_as_int(a.w);
+			L.sample = (int) cs.y;
+			L.origin = (int) (meta & 0xffffu) - 1;
+			L.eye = (int) ((meta >> 24) & 3u);
+			L.branch = __float_as_uint(dc.w);
+			L.count = cs.x;
+			if (L.phong) {
+				const float4 sp = p.litE[slot], rd = p.litF[slot];
+				L.specular = Col(sp.x, sp.y, sp.z);
+				L.exponent = sp.w;
+				L.rayDir = V3<float>(rd.x, rd.y, rd.z);
+			} else {
+				L.specular = Col(0, 0, 0);
+				L.exponent = 1;
+				L.rayDir = V3<float>(0, 0, 1);
+			}
+			sum = sum + waveEyeColor(sc, L.eye, waveLightLoop<F>(sc, ft, L, p.rp.roundKeys, p.rp.seed, stk, traced));
 		}
-		const Col c = waveLightLoop<F>(sc, ft, L, p.rp.roundKeys, p.rp.seed, stk, traced);
-		waveAccumulate(p, L.pixel, waveEyeColor(sc, L.eye, c));
+		if (pixel < 0) continue;
+		if (p.direct) waveAddDirect(p, pixel, sum);
+		else waveAccumulate(p, pixel, sum);
 	}
 	unsigned long long total = traced;
 	for (int m = 16; m > 0; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
@@ -464,7 +497,7 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 			else waveShadowKernel<F, 8><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
 		}
 	}
-	resolveWaveKernel<<<cfg.numSMs * 4, 256, 0, cfg.stream>>>(p);
+	if (!p.direct) resolveWaveKernel<<<cfg.numSMs * 4, 256, 0, cfg.stream>>>(p);
 	return cudaGetLastError();
 }
 
