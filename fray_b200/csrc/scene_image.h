@@ -591,6 +591,131 @@ template <typename R> struct SceneImage {
 		return feat;
 	}
 
+
+	// ---- alternative KD trees for the fast precision (OFF by default: FRAY_GPU_SAH_KD=1) -------------------------------------
+	// The reference splits every node at the spatial median of its box, cycling x, y, z, until 20 triangles are left or depth
+	// 64 is reached (src/mesh.cpp:315-355, src/constants.h:38-39). Those trees travel through the C ABI, the parity precision
+	// walks them literally, and the fast precision walks them too. They look like a poor structure -- the teapot of boxed /
+	// forest: depth 65, 22-30 triangle tests per walk -- so round 2 measured trees of our own over the same triangles: surface
+	// area heuristic over 32 bins per axis, leaf size and traversal cost as parameters (FRAY_KD_LEAF, FRAY_KD_CT). On the CPU
+	// model they cut the triangle tests 4x for 1.5x the inner steps; on the B200 (ms, reference trees / SAH leaf 4 / 8 / 16):
+	// boxed 2.56 / 3.16 / 2.86 / 2.71, forest 4K 1.75 / 1.75 / 1.68 / 1.71, hw9/dragon 6.55 / 6.19 / 5.83 / 5.87. A leaf's
+	// triangle loop is coherent and its loads are independent; inner steps are dependent loads and the irregular trees make
+	// neighbouring rays part ways earlier. Two of the five BASELINE configurations against one: the reference's trees stay.
+	struct SahTri { float lo[3], hi[3]; int tri; };
+
+	static void buildSahNode(const std::vector<SahTri>& tris, const float* blo, const float* bhi, int depth, size_t nodeIdx, size_t firstNode,
+	                         size_t firstRef, std::vector<DKdNode<R>>& kd, std::vector<int>& refs)
+	{
+		const int n = (int) tris.size();
+		auto makeLeaf = [&]() {
+			DKdNode<R> leaf;
+			leaf.axis = 3;
+			leaf.a = (int) refs.size(); // absolute index of the first reference
+			leaf.b = n;
+			leaf.split = 0;
+			for (const SahTri& t: tris) refs.push_back(t.tri);
+			kd[nodeIdx] = leaf;
+		};
+		static const int leafSize = getenv("FRAY_KD_LEAF") ? atoi(getenv("FRAY_KD_LEAF")) : 8;
+		static const double ctEnv = getenv("FRAY_KD_CT") ? atof(getenv("FRAY_KD_CT")) : 2.0;
+		if (n <= leafSize || depth >= 48) { makeLeaf(); return; }
+		const float ext[3] = { bhi[0] - blo[0], bhi[1] - blo[1], bhi[2] - blo[2] };
+		const double area = 2.0 * ((double) ext[0] * ext[1] + (double) ext[1] * ext[2] + (double) ext[2] * ext[0]);
+		if (!(area > 0)) { makeLeaf(); return; }
+		const int BINS = 32;
+		const double costTraverse = ctEnv, costTri = 1.5;
+		double bestCost = costTri * n; // the cost of not splitting
+		int bestAxis = -1;
+		float bestSplit = 0;
+		for (int axis = 0; axis < 3; axis++) {
+			if (!(ext[axis] > 0)) continue;
+			const float inv = (float) BINS / ext[axis];
+			int startCount[BINS] = { 0 }, endCount[BINS] = { 0 };
+			for (int i = 0; i < n; i++) {
+				const float lo = std::max(tris[i].lo[axis], blo[axis]), hi = std::min(tris[i].hi[axis], bhi[axis]);
+				int b0 = (int) ((lo - blo[axis]) * inv), b1 = (int) ((hi - blo[axis]) * inv);
+				b0 = std::min(std::max(b0, 0), BINS - 1);
+				b1 = std::min(std::max(b1, b0), BINS - 1);
+				startCount[b0]++;
+				endCount[b1]++;
+			}
+			int nLeft = 0, nEnded = 0;
+			for (int k = 1; k < BINS; k++) { // plane between bins k-1 and k
+				nLeft += startCount[k - 1];   // triangles that start below the plane
+				nEnded += endCount[k - 1];    // triangles that end below it
+				const int nRight = n - nEnded;
+				const float split = blo[axis] + ext[axis] * (float) k / (float) BINS;
+				const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+				const double wl = split - blo[axis], wr = bhi[axis] - split;
+				const double areaL = 2.0 * (wl * ext[a1] + (double) ext[a1] * ext[a2] + (double) ext[a2] * wl);
+				const double areaR = 2.0 * (wr * ext[a1] + (double) ext[a1] * ext[a2] + (double) ext[a2] * wr);
+				double cost = costTraverse + costTri * (areaL / area * nLeft + areaR / area * nRight);
+				if (nLeft == 0 || nRight == 0) cost *= 0.8; // cutting off empty space is worth a node
+				if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestSplit = split; }
+			}
+		}
+		if (bestAxis < 0) { makeLeaf(); return; }
+		std::vector<SahTri> left, right;
+		for (const SahTri& t: tris) {
+			const float lo = t.lo[bestAxis], hi = t.hi[bestAxis];
+			const bool inLeft = lo < bestSplit || hi <= bestSplit;
+			const bool inRight = hi > bestSplit || (lo >= bestSplit && !inLeft);
+			if (inLeft) left.push_back(t);
+			if (inRight) right.push_back(t);
+		}
+		if ((int) left.size() == n && (int) right.size() == n) { makeLeaf(); return; } // nothing separated
+		const size_t child = kd.size();
+		kd.push_back(DKdNode<R>());
+		kd.push_back(DKdNode<R>());
+		DKdNode<R> inner;
+		inner.axis = bestAxis;
+		inner.a = (int) child; // absolute index of children[0]; children[1] follows
+		inner.b = 0;
+		inner.split = (R) bestSplit;
+		kd[nodeIdx] = inner;
+		float lhi[3] = { bhi[0], bhi[1], bhi[2] }, rlo[3] = { blo[0], blo[1], blo[2] };
+		lhi[bestAxis] = bestSplit;
+		rlo[bestAxis] = bestSplit;
+		buildSahNode(left, blo, lhi, depth + 1, child, firstNode, firstRef, kd, refs);
+		buildSahNode(right, rlo, bhi, depth + 1, child + 1, firstNode, firstRef, kd, refs);
+	}
+
+	// replaces the KD tree of mesh m (fast precision): nodes appended to `kd`, references (relative triangle indices) to `refs`
+	static int buildSahTree(const FrayGpuScene& s, const FrayGpuMesh& m, std::vector<DKdNode<R>>& kd, std::vector<int>& refs, int& maxDepthOut)
+	{
+		std::vector<SahTri> tris;
+		tris.reserve(m.num_triangles);
+		for (int t = 0; t < m.num_triangles; t++) {
+			const size_t ti = (size_t) m.first_triangle + t;
+			const double nn = s.tri_abxac[3 * ti] * s.tri_abxac[3 * ti] + s.tri_abxac[3 * ti + 1] * s.tri_abxac[3 * ti + 1] + s.tri_abxac[3 * ti + 2] * s.tri_abxac[3 * ti + 2];
+			if (!(nn > 0)) continue; // degenerate: can never be hit (its record is all zeros)
+			SahTri st;
+			st.tri = t;
+			for (int k = 0; k < 3; k++) { st.lo[k] = FLT_MAX; st.hi[k] = -FLT_MAX; }
+			for (int c = 0; c < 3; c++) {
+				const double* v = s.vertices + 3 * ((size_t) m.first_vertex + s.tri_v[3 * ti + c]);
+				for (int k = 0; k < 3; k++) {
+					// outward rounding: the box must contain the triangle as the FP32 records see it
+					const float f = (float) v[k];
+					st.lo[k] = std::min(st.lo[k], std::nextafter(f, -FLT_MAX));
+					st.hi[k] = std::max(st.hi[k], std::nextafter(f, FLT_MAX));
+				}
+			}
+			tris.push_back(st);
+		}
+		float blo[3], bhi[3];
+		for (int k = 0; k < 3; k++) {
+			blo[k] = std::nextafter((float) m.bbox_min[k], -FLT_MAX);
+			bhi[k] = std::nextafter((float) m.bbox_max[k], FLT_MAX);
+		}
+		const size_t root = kd.size();
+		kd.push_back(DKdNode<R>());
+		buildSahNode(tris, blo, bhi, 0, root, root, refs.size(), kd, refs);
+		maxDepthOut = 48;
+		return (int) root;
+	}
+
 	bool build(const FrayGpuScene& s, std::string& err)
 	{
 		blob.clear();
@@ -726,6 +851,23 @@ template <typename R> struct SceneImage {
 				for (int i = 0; i < m.num_leaf_refs; i++)
 					if (!inRange(s.leaf_refs[(size_t) m.first_leaf_ref + i], m.num_triangles)) { err = "KD leaf reference out of range"; return false; }
 			}
+		}
+
+		if (!Num<R>::kExact && getenv("FRAY_GPU_SAH_KD")) {
+			// fast precision: our own trees over the same triangles (see buildSahTree); leaf references become absolute-in-mesh
+			// offsets exactly as in the reference layout: leaf.a indexes leafRefs, entries are relative to mesh.firstTri
+			kd.clear();
+			leafRefs.clear();
+			kdBox.clear();
+			for (int mi = 0; mi < s.num_meshes; mi++) {
+				const FrayGpuMesh& m = s.meshes[mi];
+				if (m.kd_root < 0) continue;
+				int depth = 0;
+				meshes[mi].kdRoot = buildSahTree(s, m, kd, leafRefs, depth);
+				meshes[mi].firstLeafRef = 0;
+			}
+			if (getenv("FRAY_GPU_VERBOSE")) fprintf(stderr, "fray_gpu: fast-precision KD trees: %zu nodes, %zu leaf references (reference trees: %lld nodes, %lld references)\n",
+			                                        kd.size(), leafRefs.size(), (long long) s.num_kd_nodes, (long long) s.num_leaf_refs);
 		}
 
 		std::vector<DShader<R>> shaders(s.num_shaders);
