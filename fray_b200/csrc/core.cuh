@@ -275,6 +275,9 @@ template <typename R> struct DScene {
 	// fast precision only: one 48-byte record per triangle for the KD leaves (intersectMeshFast): plane (N, N.A) with
 	// N = AB ^ AC normalised, and the two barycentric planes lambda2(p) = e2.(p,1), lambda3(p) = e3.(p,1)
 	const float4* kdTris;
+	// the same records once more in LEAF order: record r belongs to leaf reference leafRefs[r] (wave.cuh, kdWalk: a leaf's
+	// triangles are then consecutive in memory and their loads do not wait for the reference to arrive)
+	const float4* kdLeafTris;
 	// fast precision only: FRAY_LIGHT_REC_VEC float4 per light, what explicitLightSample needs in six 128-bit loads:
 	// {type, xSubd, ySubd, samples} {centre, area} {sample-grid corner, 1 / xSubd} {column step} {row step} {colour * power}
 	const float4* lightRecs;

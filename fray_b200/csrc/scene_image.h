@@ -1062,6 +1062,29 @@ template <typename R> struct SceneImage {
 			}
 		}
 
+		std::vector<float4> kdLeafTris;
+		if (!Num<R>::kExact) {
+			kdLeafTris.resize(3 * leafRefs.size());
+			for (int mi = 0; mi < s.num_meshes; mi++) {
+				if (meshes[mi].kdRoot < 0) continue;
+				// the references of mesh mi: every leaf of its tree (walk the nodes: a leaf owns [a, a + b))
+				std::vector<int> todo(1, meshes[mi].kdRoot);
+				while (!todo.empty()) {
+					const DKdNode<R> n = kd[todo.back()];
+					todo.pop_back();
+					if (n.axis == 3) {
+						for (int i = 0; i < n.b; i++) {
+							const size_t r = (size_t) n.a + i, t = (size_t) meshes[mi].firstTri + leafRefs[r];
+							for (int k = 0; k < 3; k++) kdLeafTris[3 * r + k] = kdTris[3 * t + k];
+						}
+					} else {
+						todo.push_back(n.a);
+						todo.push_back(n.a + 1);
+					}
+				}
+			}
+		}
+
 #define FRAY_PUT(member, vec) d.member = reinterpret_cast<decltype(d.member)>(append(vec))
 		FRAY_PUT(nodes, nodes);
 		FRAY_PUT(geoms, geoms);
@@ -1087,6 +1110,7 @@ template <typename R> struct SceneImage {
 		FRAY_PUT(leafRefs, leafRefs);
 		FRAY_PUT(texels, texels);
 		FRAY_PUT(kdTris, kdTris);
+		FRAY_PUT(kdLeafTris, kdLeafTris);
 		FRAY_PUT(lightRecs, lightRecs);
 		FRAY_PUT(nodeBox, nodeBox);
 		FRAY_PUT(flatPolys, flatPolys);
@@ -1106,7 +1130,7 @@ template <typename R> struct SceneImage {
 		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
 		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
 		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
-		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(lightRecs); FRAY_REBASE(nodeBox);
+		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(kdLeafTris); FRAY_REBASE(lightRecs); FRAY_REBASE(nodeBox);
 #undef FRAY_REBASE
 		return d;
 	}

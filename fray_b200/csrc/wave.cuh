@@ -89,8 +89,9 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 	int bestTri = -1;
 	float bestL2 = 0, bestL3 = 0;
 
-	auto testTriangle = [&](int t) { // Triangle::intersectFast, src/triangle.cpp:66-94, on the 48-byte plane records
-		const float4 pl = sc.kdTris[3 * (size_t) t], e2 = sc.kdTris[3 * (size_t) t + 1], e3 = sc.kdTris[3 * (size_t) t + 2];
+	// Triangle::intersectFast, src/triangle.cpp:66-94, on a 48-byte plane record; `t` is what the caller wants back on a hit
+	auto testTriangle = [&](const float4* rec, int t) {
+		const float4 pl = rec[0], e2 = rec[1], e3 = rec[2];
 		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, pl.z * dz));
 		if (cull && s > 0.0f) return;
 		const float hh = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
@@ -109,7 +110,7 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 	bool found = false;
 	if (m.kdRoot < 0) {
 		for (int t = m.firstTri; t < m.firstTri + m.numTris; t++) {
-			testTriangle(t);
+			testTriangle(sc.kdTris + 3 * (size_t) t, t);
 			if (ANYHIT && bestTri >= 0) break;
 		}
 		found = bestTri >= 0;
@@ -138,7 +139,8 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 				n = nodes[ni];
 			}
 			strict = false;
-			for (int i = 0; i < n.z; i++) testTriangle(m.firstTri + sc.leafRefs[n.y + i]);
+			// leaf: its records are consecutive in kdLeafTris; a hit remembers the reference, the triangle id is looked up at the end
+			for (int i = 0; i < n.z; i++) testTriangle(sc.kdLeafTris + 3 * (size_t) (n.y + i), n.y + i);
 			if (bestTri >= 0) {
 				if (ANYHIT) { found = true; break; }
 				// a hit inside this leaf's interval is the closest one: everything still pending starts farther away
@@ -158,7 +160,7 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 	}
 	if (!found) return false;
 	tHit = best;
-	triHit = bestTri;
+	triHit = m.kdRoot < 0 ? bestTri : m.firstTri + sc.leafRefs[bestTri]; // KD walk: bestTri is the index of the leaf reference
 	l2Hit = bestL2;
 	l3Hit = bestL3;
 	return true;
