@@ -1392,12 +1392,24 @@ template <typename R> FRAY_HD int lightNumSamples(const DLight<R>& l) { return l
 template <typename R> FRAY_HD Col lightEmission(const DLight<R>& l) { return loadCol(l.color) * l.power; } // Light::getColor
 
 // PointLight::getNthSample src/lights.cpp:31-35; RectLight::getNthSample src/lights.cpp:49-77
+// the `color` result of getNthSample: it depends on the light and the shaded point only, not on the sample (the wavefront's
+// light loop evaluates it once per light)
+template <typename R>
+FRAY_HD Col lightColorAt(const DLight<R>& l, const V3<R>& shadePos)
+{
+	if (l.type == FRAY_LIGHT_POINT) return loadCol(l.color) * l.power;
+	const V3<R> q = xfUnpoint(l.T, shadePos);
+	if (q.y > 0) return Col(0, 0, 0);
+	const float cosWeight = (float) (-q.y / length(q));
+	return loadCol(l.color) * l.power * l.areaF * cosWeight;
+}
+
 template <typename R, typename RNG>
 FRAY_HD void lightSample(const DLight<R>& l, RNG& rng, int sampleIdx, const V3<R>& shadePos, V3<R>& samplePos, Col& color, bool wantColor)
 {
 	if (l.type == FRAY_LIGHT_POINT) {
 		samplePos = load3(l.pos);
-		color = loadCol(l.color) * l.power;
+		if (wantColor) color = loadCol(l.color) * l.power;
 		return;
 	}
 	const R sx = (R) 1 / l.xSubd, sy = (R) 1 / l.ySubd;
@@ -1407,15 +1419,7 @@ FRAY_HD void lightSample(const DLight<R>& l, RNG& rng, int sampleIdx, const V3<R
 	const int column = sampleIdx - row * l.xSubd;
 	const R px = column * sx + sx * (R) rng.randfloat();
 	const R py = row * sy + sy * (R) rng.randfloat();
-	if (wantColor) {
-		const V3<R> q = xfUnpoint(l.T, shadePos);
-		if (q.y > 0) {
-			color = Col(0, 0, 0);
-		} else {
-			const float cosWeight = (float) (-q.y / length(q));
-			color = loadCol(l.color) * l.power * l.areaF * cosWeight;
-		}
-	}
+	if (wantColor) color = lightColorAt(l, shadePos);
 	samplePos = xfPoint(l.T, V3<R>(px - (R) 0.5, 0, py - (R) 0.5));
 }
 

@@ -116,6 +116,40 @@ FRAY_HD bool flatAny(const float4* __restrict__ P, int n, float ox, float oy, fl
 	return hit;
 }
 
+// Which of the first n <= 32 records can a ray that STARTS at o hit at all, whatever its direction? A record is hit from its
+// front side only (s = N.d < 0) and at t = h / s >= 0, so h = dN - N.o must not be positive: an origin behind the plane sees
+// the back. h is the very number flatTest computes (same operations, same operands), and with h > 1e-12 and s < 0 the
+// quotient cannot round to zero, so dropping those records changes no result. Every shadow ray of a light loop leaves from
+// the same point: the mask is computed once per point and light (wave.cuh), and in a closed room it is empty.
+#define FRAY_FLAT_BEHIND 1e-12f
+FRAY_HD unsigned flatOriginMask(const float4* __restrict__ P, int n, float ox, float oy, float oz)
+{
+	unsigned mask = 0;
+	for (int i = 0; i < n; i++) {
+		const float4 pl = P[FRAY_FLAT_POLY_VEC * i];
+		const float h = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
+		mask |= (h > FRAY_FLAT_BEHIND ? 0u : 1u) << i;
+	}
+	return mask;
+}
+
+// flatAny over the records whose bit is set
+FRAY_HD bool flatAnyMasked(const float4* __restrict__ P, unsigned mask, float ox, float oy, float oz, float dx, float dy, float dz, float tMax)
+{
+	bool hit = false;
+	while (mask != 0) {
+#if defined(__CUDA_ARCH__)
+		const int i = __ffs((int) mask) - 1;
+#else
+		const int i = __builtin_ctz(mask);
+#endif
+		mask &= mask - 1u;
+		float t;
+		hit |= (flatTest(P + FRAY_FLAT_POLY_VEC * i, ox, oy, oz, dx, dy, dz, t) >= 0.0f) & (t < tMax);
+	}
+	return hit;
+}
+
 // ---- two-sided records -----------------------------------------------------------------------------------------------
 // Polygons that are hit from either side -- Plane primitives (src/geometry.cpp:30-50) and the triangles of meshes without
 // back-face culling -- live in a list of their own: one record per polygon instead of a front and a back copy, tested without

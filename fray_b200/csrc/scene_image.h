@@ -1030,6 +1030,13 @@ template <typename R> struct SceneImage {
 				f = flatFeatures();
 			}
 			features |= f;
+			// the node loop of the wavefront skips from one node outside the flat table to the next: .w of a node's upper box corner
+			// holds the index of the next such node (num_nodes: none)
+			int next = s.num_nodes;
+			for (int i = s.num_nodes - 1; i >= 0; i--) {
+				memcpy(&nodeBox[2 * i + 1].w, &next, sizeof(int));
+				if (!nodes[i].inFlat) next = i;
+			}
 		}
 		for (int i = 0; i < s.num_nodes; i++)
 			if (!nodes[i].inFlat) features |= FRAY_F_NODES;

@@ -90,21 +90,22 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 	float bestL2 = 0, bestL3 = 0;
 
 	// Triangle::intersectFast, src/triangle.cpp:66-94, on a 48-byte plane record; `t` is what the caller wants back on a hit
+	// All three vectors of the record are fetched before anything is tested (one load latency per triangle instead of three in
+	// a chain) and the tests are folded into one predicate: the same operations on the same operands as the early-out form, so
+	// the same hits.
 	auto testTriangle = [&](const float4* rec, int t) {
 		const float4 pl = rec[0], e2 = rec[1], e3 = rec[2];
 		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, pl.z * dz));
-		if (cull && s > 0.0f) return;
 		const float hh = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
 		const float tt = flatDivide(hh, s);
-		if (!(tt >= 0.0f && tt <= best)) return;
 		const float px = fmaf(dx, tt, ox), py = fmaf(dy, tt, oy), pz = fmaf(dz, tt, oz);
 		const float l2 = fmaf(e2.x, px, fmaf(e2.y, py, fmaf(e2.z, pz, e2.w)));
 		const float l3 = fmaf(e3.x, px, fmaf(e3.y, py, fmaf(e3.z, pz, e3.w)));
-		if (l2 < 0.0f || l3 < 0.0f || l2 + l3 > 1.0f) return;
-		best = tt;
-		bestTri = t;
-		bestL2 = l2;
-		bestL3 = l3;
+		const bool miss = (cull && s > 0.0f) || !(tt >= 0.0f && tt <= best) || l2 < 0.0f || l3 < 0.0f || l2 + l3 > 1.0f;
+		best = miss ? best : tt;
+		bestTri = miss ? bestTri : t;
+		bestL2 = miss ? bestL2 : l2;
+		bestL3 = miss ? bestL3 : l3;
 	};
 
 	bool found = false;
@@ -263,10 +264,14 @@ FRAY_HD_HOT bool waveNodes(const DScene<float>& sc, const Ray<float>& ray, float
 	// RRay::prepareForTracing, src/bbox.h:49-54, for the world ray
 	const V3<float> inv(fabsf(ray.dir.x) > 1e-12f ? 1.0f / ray.dir.x : 1e12f, fabsf(ray.dir.y) > 1e-12f ? 1.0f / ray.dir.y : 1e12f,
 	                    fabsf(ray.dir.z) > 1e-12f ? 1.0f / ray.dir.z : 1e12f);
-	for (int n = 0; n < sc.numNodes; n++) {
+	// nodes that live in the flat table are stepped over: the upper corner of a node's box carries the index of the next node
+	// that does not (scene_image.h)
+	for (int n = 0, nextNode; n < sc.numNodes; n = nextNode) {
 		const DNode<float>& nd = sc.nodes[n];
-		if ((F & FRAY_F_FLAT) && nd.inFlat) continue;
-		if (!waveBoxHit(sc.nodeBox[2 * n], sc.nodeBox[2 * n + 1], ray, inv, ANYHIT ? maxDist : wh.t)) continue;
+		const float4 boxLo = sc.nodeBox[2 * n], boxHi = sc.nodeBox[2 * n + 1];
+		nextNode = (F & FRAY_F_FLAT) ? floatBits(boxHi.w) : n + 1;
+		if ((F & FRAY_F_FLAT) && n == 0 && nd.inFlat) continue;
+		if (!waveBoxHit(boxLo, boxHi, ray, inv, ANYHIT ? maxDist : wh.t)) continue;
 		Ray<float> local;
 		float scale;
 		waveLocalRay(nd, ray, local, scale);
@@ -335,8 +340,10 @@ FRAY_HD_HOT void waveClosest(const DScene<float>& sc, const FlatTab& ft, const R
 }
 
 // visible(), src/main.cpp:64-80 (cf. visible() in core.cuh)
+// `flatMask`: the records of the light's shadow set the start point can hit at all (waveShadowSet), or FRAY_FLAT_UNMASKED
+#define FRAY_FLAT_UNMASKED 0xffffffffu // (sets of up to 31 records are masked)
 template <int F, typename STK>
-FRAY_HD_HOT bool waveVisible(const DScene<float>& sc, const FlatTab& ft, const V3<float>& a, const V3<float>& b, int light, int origin, STK& stk)
+FRAY_HD_HOT bool waveVisible(const DScene<float>& sc, const FlatTab& ft, const V3<float>& a, const V3<float>& b, int light, int origin, STK& stk, unsigned flatMask = FRAY_FLAT_UNMASKED)
 {
 	Ray<float> ray;
 	ray.dir = b - a;
@@ -349,7 +356,9 @@ FRAY_HD_HOT bool waveVisible(const DScene<float>& sc, const FlatTab& ft, const V
 			first = sc.shadowFirst[light];
 			count = sc.shadowCount[light];
 		}
-		if (flatAny(ft.polys + FRAY_FLAT_POLY_VEC * first, count, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		if (flatMask != FRAY_FLAT_UNMASKED) {
+			if (flatAnyMasked(ft.polys + FRAY_FLAT_POLY_VEC * first, flatMask, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
+		} else if (flatAny(ft.polys + FRAY_FLAT_POLY_VEC * first, count, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
 		if (F & FRAY_F_HEX) {
 			const unsigned hexMask = (light >= 0 && light < FRAY_SHADOW_LIGHTS) ? sc.shadowHex[light] : 0xffffffffu;
 			if (flatHexAny(ft.hexes, sc.numFlatHex, hexMask, ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z, maxDist)) return false;
@@ -550,13 +559,24 @@ FRAY_HD_HOT Col waveLightLoop(const DScene<float>& sc, const FlatTab& ft, const 
 	for (int li = 0; li < sc.numLights; li++) {
 		const DLight<float>& light = sc.lights[li];
 		const int ns = lightNumSamples(light);
+		const Col lightCol = lightColorAt(light, L.ip); // the same for every sample of the light
+		// every shadow ray of this loop starts at shadowStart: the records of the light's shadow set it lies behind are out
+		unsigned flatMask = FRAY_FLAT_UNMASKED;
+		if constexpr ((F & FRAY_F_FLAT) != 0) {
+			int first = 0, count = sc.numFlatGeom;
+			if (li < FRAY_SHADOW_LIGHTS && sc.shadowCount[li] >= 0) {
+				first = sc.shadowFirst[li];
+				count = sc.shadowCount[li];
+			}
+			if (count <= 31) flatMask = flatOriginMask(ft.polys + FRAY_FLAT_POLY_VEC * first, count, shadowStart.x, shadowStart.y, shadowStart.z);
+		}
 		Col sum(0, 0, 0);
 		for (int si = 0; si < ns; si++) {
-			Col lightCol;
+			Col unused;
 			V3<float> lightPos;
-			lightSample(light, rng, si, L.ip, lightPos, lightCol, true);
+			lightSample(light, rng, si, L.ip, lightPos, unused, false);
 			shadowRays++;
-			if (!waveVisible<F>(sc, ft, shadowStart, lightPos, li, L.origin, stk)) continue;
+			if (!waveVisible<F>(sc, ft, shadowStart, lightPos, li, L.origin, stk, flatMask)) continue;
 			const V3<float> toL = lightPos - L.ip;
 			const float distSqr = lengthSqr(toL);
 			const V3<float> toLight = normalized(toL);

@@ -19,7 +19,7 @@ EMUL_DIR = os.path.join(fb.REPO_ROOT, "tests", "emul")
 def emul():
     so = os.path.join(EMUL_DIR, "libfray_emul.so")
     src = os.path.join(EMUL_DIR, "kernel_emul.cpp")
-    deps = [src] + [os.path.join(fb.REPO_ROOT, "fray_b200", "csrc", f) for f in ("core.cuh", "flat.cuh", "rng.cuh", "scene_image.h")]
+    deps = [src] + [os.path.join(fb.REPO_ROOT, "fray_b200", "csrc", f) for f in ("core.cuh", "flat.cuh", "rng.cuh", "scene_image.h", "wave.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-x", "c++", src,
                                "-o", so, "-lpthread"])
@@ -71,3 +71,32 @@ def test_device_core_csg_layered_scene(emul, data_dir):
     assert frac >= 0.999, (frac, rmse, mx)
     aov, _ = emul(sc, fb.FP32, mode=fb.RENDER_AOV)
     assert (aov[..., 0].astype(int) == node).mean() >= 0.998
+
+
+@pytest.fixture(scope="module")
+def emul_wave(emul):
+    lib = C.CDLL(os.path.join(EMUL_DIR, "libfray_emul.so"))
+    lib.fray_emul_render_wave.argtypes = [C.c_void_p, C.POINTER(fb.FrayFrame), C.c_void_p, C.POINTER(fb.FrayStats), C.c_int]
+
+    def render(scene, kd_short=0, **kw):
+        out = np.empty((scene.height, scene.width, 3), np.float32)
+        frame, stats = fb.make_frame(**kw), fb.FrayStats()
+        assert lib.fray_emul_render_wave(scene.flat, C.byref(frame), out.ctypes.data, C.byref(stats), kd_short) == 0
+        return out, fb.RenderStats.of(stats)
+    return render
+
+
+@pytest.mark.parametrize("name", ["boxed", "forest", "forest_aa", "forest_stereo_dof", "dragon"])
+def test_wavefront_stages_match_the_megakernel(name, emul, emul_wave, golden_cases, data_dir):
+    """The wavefront stages of the fast precision (csrc/wave.cuh: trace / shade / shadow over queues, the KD short stack, the
+    light loop with its per-point record mask) against the recursion-as-a-task-stack form of core.cuh on the same scenes: the
+    same rays one for one, the same frame up to the order of FP32 additions -- also with a two-entry short stack, which forces
+    kd-restarts on every deep walk."""
+    path, seed = golden_scene(golden_cases, name)
+    sc = fb.Scene(path)
+    want, wstats = emul(sc, fb.FP32, seed=seed)
+    for kd_short in (0, 2):
+        got, stats = emul_wave(sc, kd_short, seed=seed)
+        frac, rmse, mx = ou.compare(want, got, 1e-5)
+        assert frac >= 0.9999 and rmse < 1e-5, (kd_short, frac, rmse, mx)
+        assert stats.rays == wstats.rays and stats.shadow_rays == wstats.shadow_rays
