@@ -119,7 +119,7 @@ def gpu_lib() -> C.CDLL:
     """libfray_gpu.so -- the CUDA renderer. Raises if it was not built (there is no fallback)."""
     global _gpu
     if _gpu is None:
-        path = os.path.join(_HERE, "libfray_gpu.so")
+        path = os.environ.get("FRAY_GPU_LIB") or os.path.join(_HERE, "libfray_gpu.so")  # FRAY_GPU_LIB: another build of the same library (A/B timing of kernel variants, tools/build_variant.py)
         if not os.path.exists(path):
             raise FrayError(f"{path} is missing: the CUDA back end must be built with nvcc (see __graft_entry__.build); "
                             "fray_b200 has no CPU render path")

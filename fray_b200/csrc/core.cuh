@@ -278,6 +278,10 @@ template <typename R> struct DScene {
 	// the same records once more in LEAF order: record r belongs to leaf reference leafRefs[r] (wave.cuh, kdWalk: a leaf's
 	// triangles are then consecutive in memory and their loads do not wait for the reference to arrive)
 	const float4* kdLeafTris;
+	// fast precision only: the bounding box of the triangles of every KD leaf, two vectors {min, -} {max, -} per leaf, padded;
+	// a leaf node carries the index of its box in the `split` word. The reference's trees split cells at the spatial median
+	// down to 20 triangles: most rays that cross a leaf cell pass its triangles by, and the box says so before they are tested.
+	const float4* kdLeafBox;
 	// fast precision only: FRAY_LIGHT_REC_VEC float4 per light, what explicitLightSample needs in six 128-bit loads:
 	// {type, xSubd, ySubd, samples} {centre, area} {sample-grid corner, 1 / xSubd} {column step} {row step} {colour * power}
 	const float4* lightRecs;

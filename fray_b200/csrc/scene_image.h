@@ -1069,21 +1069,37 @@ template <typename R> struct SceneImage {
 			}
 		}
 
-		std::vector<float4> kdLeafTris;
+		std::vector<float4> kdLeafTris, kdLeafBox;
 		if (!Num<R>::kExact) {
 			kdLeafTris.resize(3 * leafRefs.size());
 			for (int mi = 0; mi < s.num_meshes; mi++) {
 				if (meshes[mi].kdRoot < 0) continue;
+				const FrayGpuMesh& m = s.meshes[mi];
 				// the references of mesh mi: every leaf of its tree (walk the nodes: a leaf owns [a, a + b))
 				std::vector<int> todo(1, meshes[mi].kdRoot);
 				while (!todo.empty()) {
-					const DKdNode<R> n = kd[todo.back()];
+					const int ni = todo.back();
+					const DKdNode<R> n = kd[ni];
 					todo.pop_back();
 					if (n.axis == 3) {
+						double lo[3] = { 1e30, 1e30, 1e30 }, hi[3] = { -1e30, -1e30, -1e30 };
 						for (int i = 0; i < n.b; i++) {
 							const size_t r = (size_t) n.a + i, t = (size_t) meshes[mi].firstTri + leafRefs[r];
 							for (int k = 0; k < 3; k++) kdLeafTris[3 * r + k] = kdTris[3 * t + k];
+							const size_t ti = (size_t) m.first_triangle + leafRefs[r];
+							for (int c = 0; c < 3; c++) {
+								const double* v = s.vertices + 3 * ((size_t) m.first_vertex + s.tri_v[3 * ti + c]);
+								for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], v[k]); hi[k] = std::max(hi[k], v[k]); }
+							}
 						}
+						// the leaf's box (kdWalk tests it before the triangles), padded far beyond what FP32 can move a hit point
+						double ext = 0;
+						for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+						const double pad = n.b > 0 ? 1e-4 * ext + 1e-6 : 0.0;
+						const int box = (int) (kdLeafBox.size() / 2);
+						kdLeafBox.push_back(float4{ (float) (lo[0] - pad), (float) (lo[1] - pad), (float) (lo[2] - pad), 0.0f });
+						kdLeafBox.push_back(float4{ (float) (hi[0] + pad), (float) (hi[1] + pad), (float) (hi[2] + pad), 0.0f });
+						memcpy(&kd[ni].split, &box, sizeof(int)); // (R is float here)
 					} else {
 						todo.push_back(n.a);
 						todo.push_back(n.a + 1);
@@ -1118,6 +1134,7 @@ template <typename R> struct SceneImage {
 		FRAY_PUT(texels, texels);
 		FRAY_PUT(kdTris, kdTris);
 		FRAY_PUT(kdLeafTris, kdLeafTris);
+		FRAY_PUT(kdLeafBox, kdLeafBox);
 		FRAY_PUT(lightRecs, lightRecs);
 		FRAY_PUT(nodeBox, nodeBox);
 		FRAY_PUT(flatPolys, flatPolys);
@@ -1137,7 +1154,7 @@ template <typename R> struct SceneImage {
 		FRAY_REBASE(triA); FRAY_REBASE(triAB); FRAY_REBASE(triAC); FRAY_REBASE(triN); FRAY_REBASE(triG);
 		FRAY_REBASE(triDndx); FRAY_REBASE(triDndy); FRAY_REBASE(triNi); FRAY_REBASE(triTi);
 		FRAY_REBASE(normals); FRAY_REBASE(uvs); FRAY_REBASE(kd); FRAY_REBASE(kdBox); FRAY_REBASE(leafRefs); FRAY_REBASE(texels);
-		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(kdLeafTris); FRAY_REBASE(lightRecs); FRAY_REBASE(nodeBox);
+		FRAY_REBASE(flatPolys); FRAY_REBASE(flatInfo); FRAY_REBASE(kdTris); FRAY_REBASE(kdLeafTris); FRAY_REBASE(kdLeafBox); FRAY_REBASE(lightRecs); FRAY_REBASE(nodeBox);
 #undef FRAY_REBASE
 		return d;
 	}

@@ -91,21 +91,32 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 
 	// Triangle::intersectFast, src/triangle.cpp:66-94, on a 48-byte plane record; `t` is what the caller wants back on a hit
 	// All three vectors of the record are fetched before anything is tested (one load latency per triangle instead of three in
-	// a chain) and the tests are folded into one predicate: the same operations on the same operands as the early-out form, so
-	// the same hits.
+	// a chain) and the tests are folded into one minimum, as flatTest does: the hit counts iff
+	//     min(l2, l3, 1 - (l2 + l3), t, [culling: -s]) >= 0   and   t <= best.
+	// Same operations on the same operands as the early-out form, and the folded tests decide exactly as the separate ones:
+	// 1 - x is exact for x in [1/2, 2] and keeps the sign outside, fminf passes -0 as "not negative" just as `< 0` does, and a
+	// NaN or infinite t (a ray in the triangle's plane) fails `t <= best`.
+	const float cullSign = cull ? -1.0f : 0.0f;
 	auto testTriangle = [&](const float4* rec, int t) {
 		const float4 pl = rec[0], e2 = rec[1], e3 = rec[2];
 		const float s = fmaf(pl.x, dx, fmaf(pl.y, dy, pl.z * dz));
 		const float hh = fmaf(-pl.x, ox, fmaf(-pl.y, oy, fmaf(-pl.z, oz, pl.w)));
 		const float tt = flatDivide(hh, s);
+		if constexpr (ANYHIT) {
+			// most triangles an occlusion walk meets are missed by every lane: the plane test alone decides that (the two edge
+			// vectors are in flight already)
+			if (!((fminf(tt, cullSign * s) >= 0.0f) & (tt <= best))) return;
+		}
 		const float px = fmaf(dx, tt, ox), py = fmaf(dy, tt, oy), pz = fmaf(dz, tt, oz);
 		const float l2 = fmaf(e2.x, px, fmaf(e2.y, py, fmaf(e2.z, pz, e2.w)));
 		const float l3 = fmaf(e3.x, px, fmaf(e3.y, py, fmaf(e3.z, pz, e3.w)));
-		const bool miss = (cull && s > 0.0f) || !(tt >= 0.0f && tt <= best) || l2 < 0.0f || l3 < 0.0f || l2 + l3 > 1.0f;
-		best = miss ? best : tt;
-		bestTri = miss ? bestTri : t;
-		bestL2 = miss ? bestL2 : l2;
-		bestL3 = miss ? bestL3 : l3;
+		const float inside = fminf(fminf(l2, l3), 1.0f - (l2 + l3));
+		const float margin = fminf(fminf(inside, tt), cullSign * s);
+		const bool hit = (margin >= 0.0f) & (tt <= best);
+		best = hit ? tt : best;
+		bestTri = hit ? t : bestTri;
+		bestL2 = hit ? l2 : bestL2;
+		bestL3 = hit ? l3 : bestL3;
 	};
 
 	bool found = false;
@@ -141,7 +152,19 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 			}
 			strict = false;
 			// leaf: its records are consecutive in kdLeafTris; a hit remembers the reference, the triangle id is looked up at the end
-			for (int i = 0; i < n.z; i++) testTriangle(sc.kdLeafTris + 3 * (size_t) (n.y + i), n.y + i);
+			// ... if the ray touches the box of the leaf's triangles within [0, best] at all (DScene::kdLeafBox, padded: "no" is safe)
+			bool touches = n.z > 0;
+			if (touches) {
+				const float4 lo = sc.kdLeafBox[2 * (size_t) n.w], hi = sc.kdLeafBox[2 * (size_t) n.w + 1];
+				const float ax0 = (lo.x - ox) * rx, ax1 = (hi.x - ox) * rx;
+				const float ay0 = (lo.y - oy) * ry, ay1 = (hi.y - oy) * ry;
+				const float az0 = (lo.z - oz) * rz, az1 = (hi.z - oz) * rz;
+				const float tn = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+				const float tf = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best));
+				touches = tn <= tf;
+			}
+			if (touches)
+				for (int i = 0; i < n.z; i++) testTriangle(sc.kdLeafTris + 3 * (size_t) (n.y + i), n.y + i);
 			if (bestTri >= 0) {
 				if (ANYHIT) { found = true; break; }
 				// a hit inside this leaf's interval is the closest one: everything still pending starts farther away

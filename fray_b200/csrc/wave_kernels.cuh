@@ -73,6 +73,15 @@ struct WaveParams {
 };
 
 #if defined(FRAY_WAVE_IMPL) // the kernels themselves: render_wave.cu only (fray_gpu.cu needs the parameter block and the launcher)
+// Queue entries are written once and read once, each by one thread: streaming accesses (evict-first), so that they do not push
+// the KD nodes and triangle records -- which every warp walks again and again -- out of the L1 and the L2.
+#if defined(FRAY_WAVE_NO_STREAM)
+template <typename T> __device__ __forceinline__ T qld(const T* p) { return *p; }
+template <typename T> __device__ __forceinline__ void qst(T* p, const T& v) { *p = v; }
+#else
+template <typename T> __device__ __forceinline__ T qld(const T* p) { return __ldcs(p); }
+template <typename T> __device__ __forceinline__ void qst(T* p, const T& v) { __stcs(p, v); }
+#endif
 // KD short stack in shared memory: entry i of this thread at column[i * 128] (conflict-free: consecutive lanes, consecutive words)
 struct KdStoreShared {
 	uint2* column;
@@ -187,29 +196,29 @@ struct WaveSink {
 		const unsigned slot = wavePush(p.ctr + FRAY_WCTR_RAYS + ((p.wave + 1) * FRAY_WAVE_REGIONS + region) * FRAY_WAVE_CTR_STRIDE);
 		if (slot >= cap) { p.ctr[FRAY_WCTR_OVERFLOW] = 1; return; }
 		const size_t i = (size_t) ((p.wave + 1) & 1) * p.rayCap + (size_t) region * cap + slot;
-		p.rayO[i] = make_float4(c.start.x, c.start.y, c.start.z, __int_as_float(c.pixel));
-		p.rayD[i] = make_float4(c.dir.x, c.dir.y, c.dir.z, __uint_as_float(waveMeta(c.origin, c.depth, c.eye, 0)));
-		p.rayW[i] = make_float4(c.weight.r, c.weight.g, c.weight.b, __uint_as_float(c.branch));
-		p.rayC[i] = make_uint2(c.count, (unsigned) c.sample);
+		qst(p.rayO + i, make_float4(c.start.x, c.start.y, c.start.z, __int_as_float(c.pixel)));
+		qst(p.rayD + i, make_float4(c.dir.x, c.dir.y, c.dir.z, __uint_as_float(waveMeta(c.origin, c.depth, c.eye, 0))));
+		qst(p.rayW + i, make_float4(c.weight.r, c.weight.g, c.weight.b, __uint_as_float(c.branch)));
+		qst(p.rayC + i, make_uint2(c.count, (unsigned) c.sample));
 	}
 	__device__ __forceinline__ void lit(const WaveLit& L)
 	{
 		if (litUsed >= p.litPerRay) { p.ctr[FRAY_WCTR_OVERFLOW] = 2; return; } // cannot happen: litPerRay is the scene's maximum
 		const unsigned slot = litBase + (unsigned) litUsed++;
-		p.litA[slot] = make_float4(L.ip.x, L.ip.y, L.ip.z, __int_as_float(L.pixel));
-		p.litB[slot] = make_float4(L.n.x, L.n.y, L.n.z, __uint_as_float(waveMeta(L.origin, 0, L.eye, L.phong)));
-		p.litC[slot] = make_float4(L.diffuse.r, L.diffuse.g, L.diffuse.b, __uint_as_float(L.branch));
-		p.litD[slot] = make_uint2(L.count, (unsigned) L.sample);
+		qst(p.litA + slot, make_float4(L.ip.x, L.ip.y, L.ip.z, __int_as_float(L.pixel)));
+		qst(p.litB + slot, make_float4(L.n.x, L.n.y, L.n.z, __uint_as_float(waveMeta(L.origin, 0, L.eye, L.phong))));
+		qst(p.litC + slot, make_float4(L.diffuse.r, L.diffuse.g, L.diffuse.b, __uint_as_float(L.branch)));
+		qst(p.litD + slot, make_uint2(L.count, (unsigned) L.sample));
 		if (L.phong) {
-			p.litE[slot] = make_float4(L.specular.r, L.specular.g, L.specular.b, L.exponent);
-			p.litF[slot] = make_float4(L.rayDir.x, L.rayDir.y, L.rayDir.z, 0.0f);
+			qst(p.litE + slot, make_float4(L.specular.r, L.specular.g, L.specular.b, L.exponent));
+			qst(p.litF + slot, make_float4(L.rayDir.x, L.rayDir.y, L.rayDir.z, 0.0f));
 		}
 	}
 	// start the lit-record slots of ray i / close them (mark what was not used)
 	__device__ __forceinline__ void begin(unsigned i) { litBase = i * (unsigned) p.litPerRay; litUsed = 0; known = Col(0, 0, 0); }
 	__device__ __forceinline__ void end()
 	{
-		for (int k = litUsed; k < p.litPerRay; k++) p.litA[litBase + (unsigned) k] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+		for (int k = litUsed; k < p.litPerRay; k++) qst(p.litA + litBase + (unsigned) k, make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1)));
 	}
 };
 
@@ -225,8 +234,8 @@ __device__ __forceinline__ bool wavePrimarySlot(const WaveParams& p, unsigned i,
 __device__ __forceinline__ void waveLoadRay(const WaveParams& p, unsigned slot, WaveRay& r)
 {
 	const size_t k = (size_t) (p.wave & 1) * p.rayCap + slot;
-	const float4 o = p.rayO[k], d = p.rayD[k], w = p.rayW[k];
-	const uint2 c = p.rayC[k];
+	const float4 o = qld(p.rayO + k), d = qld(p.rayD + k), w = qld(p.rayW + k);
+	const uint2 c = qld(p.rayC + k);
 	const unsigned meta = __float_as_uint(d.w);
 	r.start = V3<float>(o.x, o.y, o.z);
 	r.dir = V3<float>(d.x, d.y, d.z);
@@ -285,8 +294,11 @@ __device__ __forceinline__ unsigned waveRayCount(const WaveParams& p, unsigned* 
 }
 
 // ---- TRACE -----------------------------------------------------------------------------------------------------------------
+#ifndef FRAY_WAVE_TRACE_CTAS
+#define FRAY_WAVE_TRACE_CTAS 8
+#endif
 template <int F>
-__global__ void __launch_bounds__(128, 8) waveTraceKernel(const DScene<float> sc, const WaveParams p)
+__global__ void __launch_bounds__(128, FRAY_WAVE_TRACE_CTAS) waveTraceKernel(const DScene<float> sc, const WaveParams p)
 {
 	const FlatTab ft = stageFlat<float, F>(sc);
 	KdStackShared stk = waveStack(p);
@@ -311,15 +323,15 @@ __global__ void __launch_bounds__(128, 8) waveTraceKernel(const DScene<float> sc
 			ray.dir = l.dir;
 		} else {
 			const size_t k = (size_t) (p.wave & 1) * p.rayCap + waveSlot(prefix, p.rayCap / FRAY_WAVE_REGIONS, i);
-			const float4 o = p.rayO[k], d = p.rayD[k];
+			const float4 o = qld(p.rayO + k), d = qld(p.rayD + k);
 			ray.start = V3<float>(o.x, o.y, o.z);
 			ray.dir = V3<float>(d.x, d.y, d.z);
 			origin = (int) (__float_as_uint(d.w) & 0xffffu) - 1;
 		}
 		WaveHit wh;
 		waveClosest<F>(sc, ft, ray, origin, stk, wh);
-		p.hitA[i] = make_float4(wh.t, wh.l2, wh.l3, __int_as_float(wh.node));
-		p.hitB[i] = make_int2(wh.tri, wh.flat);
+		qst(p.hitA + i, make_float4(wh.t, wh.l2, wh.l3, __int_as_float(wh.node)));
+		qst(p.hitB + i, make_int2(wh.tri, wh.flat));
 		traced++;
 	}
 	unsigned long long total = traced;
@@ -353,8 +365,8 @@ __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc
 		} else {
 			waveLoadRay(p, waveSlot(prefix, p.rayCap / FRAY_WAVE_REGIONS, i), r);
 		}
-		const float4 ha = p.hitA[i];
-		const int2 hb = p.hitB[i];
+		const float4 ha = qld(p.hitA + i);
+		const int2 hb = qld(p.hitB + i);
 		WaveHit wh;
 		wh.t = ha.x; wh.l2 = ha.y; wh.l3 = ha.z; wh.node = __float_as_int(ha.w); wh.tri = hb.x; wh.flat = hb.y;
 		uint32_t count = r.count;
@@ -394,10 +406,10 @@ __global__ void __launch_bounds__(128, CTAS) waveShadowKernel(const DScene<float
 		int pixel = -1;
 		for (int k = 0; k < p.litPerRay; k++) {
 			const size_t slot = (size_t) ray * (unsigned) p.litPerRay + (unsigned) k;
-			const float4 a = p.litA[slot];
+			const float4 a = qld(p.litA + slot);
 			if (__float_as_int(a.w) < 0) break; // unused slot: a ray fills its slots from the front
-			const float4 nb = p.litB[slot], dc = p.litC[slot];
-			const uint2 cs = p.litD[slot];
+			const float4 nb = qld(p.litB + slot), dc = qld(p.litC + slot);
+			const uint2 cs = qld(p.litD + slot);
 			const unsigned meta = __float_as_uint(nb.w);
 			WaveLit L;
 			L.ip = V3<float>(a.x, a.y, a.z);
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(128, CTAS) waveShadowKernel(const DScene<float
 			L.branch = __float_as_uint(dc.w);
 			L.count = cs.x;
 			if (L.phong) {
-				const float4 sp = p.litE[slot], rd = p.litF[slot];
+				const float4 sp = qld(p.litE + slot), rd = qld(p.litF + slot);
 				L.specular = Col(sp.x, sp.y, sp.z);
 				L.exponent = sp.w;
 				L.rayDir = V3<float>(rd.x, rd.y, rd.z);
