@@ -154,6 +154,7 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 			// leaf: its records are consecutive in kdLeafTris; a hit remembers the reference, the triangle id is looked up at the end
 			// ... if the ray touches the box of the leaf's triangles within [0, best] at all (DScene::kdLeafBox, padded: "no" is safe)
 			bool touches = n.z > 0;
+#if !defined(FRAY_KD_NO_LEAFBOX)
 			if (touches) {
 				const float4 lo = sc.kdLeafBox[2 * (size_t) n.w], hi = sc.kdLeafBox[2 * (size_t) n.w + 1];
 				const float ax0 = (lo.x - ox) * rx, ax1 = (hi.x - ox) * rx;
@@ -163,6 +164,7 @@ FRAY_HD_HOT bool kdWalk(const DScene<float>& sc, const DMesh<float>& m, const Ra
 				const float tf = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best));
 				touches = tn <= tf;
 			}
+#endif
 			if (touches)
 				for (int i = 0; i < n.z; i++) testTriangle(sc.kdLeafTris + 3 * (size_t) (n.y + i), n.y + i);
 			if (bestTri >= 0) {

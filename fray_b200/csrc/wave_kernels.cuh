@@ -388,6 +388,9 @@ __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc
 // Compiled for CTAS resident CTAs per SM: 8 (64 registers, ~260 bytes of spills inside the light loop) where a record means one
 // or two shadow rays and occupancy hides the record fetch, 6 (80 registers) where it means many (area lights: boxed 2.81 -> 2.51 ms,
 // while forest and dragon lose 2-3 % with it).
+#ifndef FRAY_WAVE_SHADOW_MANY
+#define FRAY_WAVE_SHADOW_MANY 8 // shadow rays per lit record from which the 6-CTA build is used
+#endif
 template <int F, int CTAS>
 __global__ void __launch_bounds__(128, CTAS) waveShadowKernel(const DScene<float> sc, const WaveParams p)
 {
@@ -496,7 +499,7 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 		cudaFuncSetAttribute(waveShadeKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) flat);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occTrace, waveTraceKernel<F>, 128, flat + stack);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F>, 128, flat);
-		if (sc.lightSamples >= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 6>, 128, flat + stack);
+		if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 6>, 128, flat + stack);
 		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 8>, 128, flat + stack);
 		if (cfg.occTrace < 1 || cfg.occShade < 1 || cfg.occShadow < 1) return cudaErrorLaunchOutOfResources;
 	}
@@ -505,7 +508,7 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 		waveTraceKernel<F><<<cfg.numSMs * cfg.occTrace, 128, flat + stack, cfg.stream>>>(sc, p);
 		waveShadeKernel<F><<<cfg.numSMs * cfg.occShade, 128, flat, cfg.stream>>>(sc, p);
 		if (sc.numLights > 0) {
-			if (sc.lightSamples >= 8) waveShadowKernel<F, 6><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
+			if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) waveShadowKernel<F, 6><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
 			else waveShadowKernel<F, 8><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
 		}
 	}
