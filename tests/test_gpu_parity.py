@@ -331,3 +331,51 @@ def test_cli_frame_loop_with_camera_moves(tmp_path, data_dir):
             assert not np.array_equal(got, prev)
         prev = got
     ctx.close()
+
+
+def audit_hit_ids(gaov, waov):
+    """Primary hit ids of the fast precision against the oracle's, pixel by pixel. A pixel where (node, triangle) differ is
+    an EDGE TIE iff the primitive the GPU reports is one the oracle itself sees through a neighbouring pixel (or the other way
+    round): the pixel centre sits on the border between the two, and which side wins is a rounding matter -- or iff both
+    report the same node at the same depth (to 1e-4): two triangles of one mesh that meet under the pixel centre. Returns the
+    mismatching pixels as (y, x, oracle ids, gpu ids, tie?)."""
+    gi, wi = gaov[..., :2].astype(np.int64), waov[..., :2].astype(np.int64)
+    H, W = gi.shape[:2]
+    rows = []
+    for y, x in zip(*np.nonzero((gi != wi).any(axis=-1))):
+        y0, y1, x0, x1 = max(y - 1, 0), min(y + 2, H), max(x - 1, 0), min(x + 2, W)
+        near_oracle = {tuple(v) for v in wi[y0:y1, x0:x1].reshape(-1, 2)}
+        near_gpu = {tuple(v) for v in gi[y0:y1, x0:x1].reshape(-1, 2)}
+        tie = tuple(gi[y, x]) in near_oracle or tuple(wi[y, x]) in near_gpu
+        # ... or both see the same node at the same depth: two triangles that meet under the pixel centre
+        if not tie and gi[y, x, 0] == wi[y, x, 0] and gi[y, x, 0] >= 0:
+            tie = abs(float(gaov[y, x, 2]) - float(waov[y, x, 2])) <= 1e-4 * abs(float(waov[y, x, 2]))
+        rows.append((int(y), int(x), tuple(int(v) for v in wi[y, x]), tuple(int(v) for v in gi[y, x]), bool(tie)))
+    return rows
+
+
+@pytest.mark.parametrize("name,settings", [("boxed", None), ("zaphod", None), ("forest", dict(interactive="off", frameWidth=960, frameHeight=540)),
+                                           ("hw9/dragon", None)])
+def test_fp32_primary_hit_ids_differ_only_at_audited_edge_ties(name, settings, data_dir):
+    """north_star: "primary-ray hit IDs must match except audited edge ties" -- at the scenes' own resolutions (the goldens
+    are small crops), node AND triangle id of every primary ray, fast precision against the oracle. Every mismatch must pass
+    the audit (audit_hit_ids) and there may be at most 0.2 % of them; the list goes to gpurun_out/ for profiles/."""
+    import json
+    import os
+    from fray_b200 import scenes as sc_mod
+    sc = fb.Scene(sc_mod.override_scene(name, "audit", settings))
+    waov, _ = ou.oracle_render(sc, mode=fb.RENDER_AOV)
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    gaov, _ = ctx.render(mode=fb.RENDER_AOV)
+    ctx.close()
+    rows = audit_hit_ids(gaov, waov)
+    total = waov.shape[0] * waov.shape[1]
+    out = os.path.join(fb.REPO_ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"edge_ties_{name.replace('/', '_')}.json"), "w") as f:
+            json.dump(dict(scene=name, width=sc.width, height=sc.height, pixels=total, mismatches=len(rows), not_ties=sum(not r[4] for r in rows),
+                           rows=[dict(y=r[0], x=r[1], oracle=r[2], gpu=r[3], tie=r[4]) for r in rows[:200]]), f)
+    assert len(rows) <= 0.002 * total, (len(rows), total)
+    assert all(r[4] for r in rows), [r for r in rows if not r[4]][:10]
+    hit = (waov[..., 0] >= 0) & (gaov[..., 0] == waov[..., 0]) & (gaov[..., 1] == waov[..., 1])
+    np.testing.assert_allclose(gaov[..., 2][hit], waov[..., 2][hit], rtol=2e-4)
