@@ -256,8 +256,10 @@ def main():
     ap.add_argument("--config", default=HEADLINE, choices=sorted(CONFIGS), help="BASELINE.json configuration (c3 = cornell_box 256 paths/pixel, the headline)")
     ap.add_argument("--spp", type=int, default=0, help="override the paths per pixel of a path-traced configuration")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
-    ap.add_argument("--split", default="auto", choices=["tiles", "p2p", "samples", "auto"],
-                    help="multi-GPU decomposition: tiles (BASELINE.json for cornell; NCCL reduce), p2p (tiles written straight into rank 0's frame), samples")
+    ap.add_argument("--split", default="auto", choices=["tiles", "p2p", "samples", "host", "auto"],
+                    help="multi-GPU decomposition: tiles (BASELINE.json for cornell; NCCL reduce), p2p (tiles written straight into rank 0's frame), "
+                         "samples, host (end to end: every GPU stores its tiles straight into one shared page-locked host frame; device-timed: "
+                         "samples or tiles by sample count). auto = host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
@@ -295,7 +297,7 @@ def main():
     precision = fb.FP32 if args.precision == "fp32" else fb.FP64
     scene = fb.Scene(scene_file(cfg))
     W, H, spp = scene.width, scene.height, scene.spp
-    r = fdist.DistributedRenderer(scene, mode=args.split, precision=precision, device=local_rank)
+    r = fdist.DistributedRenderer(scene, mode="host" if (args.split == "auto" and world > 1) else args.split, precision=precision, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -331,7 +333,7 @@ def main():
         st = r.stats()  # syncs; per-step kernel time + ray counters of this rank
         kernel_ms.append(st.device_ms)
         rays_step = st.rays
-        launches_step = st.kernel_launches + (1 if (rank == 0 and r.mode != "p2p") else 0)  # this rank's render kernels, and resolve on rank 0
+        launches_step = st.kernel_launches + (1 if (rank == 0 and r.device_mode != "p2p") else 0)  # this rank's render kernels, and resolve on rank 0
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -373,6 +375,9 @@ def main():
         e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - te0) * 1e3 / args.steps
+    if os.environ.get("FRAY_DIST_DEBUG") and getattr(r, "dbg", None):
+        import numpy as _np
+        log("host-mode phases (us): wait-entry, launch, sync, wait-peers =", _np.round(_np.mean(_np.array(r.dbg[-args.steps:]), axis=0), 1), "kernel ms", r.stats().device_ms)
     e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -386,7 +391,8 @@ def main():
         d = np.abs(single.astype(np.float64) - frame_np.astype(np.float64))
         multi_check = {"against": "the same frame rendered by rank 0's GPU alone (same seed)", "max_abs_diff": float(d.max()),
                        "bit_identical": bool(np.array_equal(single, frame_np)), "frac_within_1e-5": float((d.max(axis=-1) <= 1e-5).mean()),
-                       "note": "tile splits are bit-identical; a sample split regroups the FP32 partial sums of a pixel"}
+                       "note": "the frame of the end-to-end path; a share cuts a pixel's samples into other chunks than one GPU does (FP32 regrouping, ~1e-5); "
+                               "fray_gpu_multi_render's tile split keeps the single GPU's chunks and is bit-identical (single_process below)"}
 
     # ---- multi-GPU, ONE process: fray_gpu_multi_render on the same N GPUs (the C++ drop-in's own path), rank 0 only ----
     single_process = None
@@ -448,7 +454,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if precision == fb.FP32 else "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, W, H), "rays_per_frame": int(rays_frame),
-                       "split": r.mode if world > 1 else "none", "l2": "flushed between timed frames (256 MB write)", "seed": 42},
+                       "split": (r.device_mode if world > 1 else "none"),
+                       "e2e_split": ("tiles, every GPU storing its own straight into one shared page-locked host frame (fray_gpu_render_to_host)"
+                                     if r.mode == "host" else (r.mode if world > 1 else "none")), "l2": "flushed between timed frames (256 MB write)", "seed": 42},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * 12},
             "gpu_launches": args.steps * launches_step,

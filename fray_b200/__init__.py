@@ -131,6 +131,9 @@ def gpu_lib() -> C.CDLL:
         L.fray_gpu_update_camera.argtypes = [C.c_void_p, C.POINTER(FrayCamera)]
         L.fray_gpu_render.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.POINTER(FrayStats)]
         L.fray_gpu_render_device.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.c_void_p]
+        L.fray_gpu_render_to_host.argtypes = [C.c_void_p, C.POINTER(FrayFrame), C.c_void_p, C.c_void_p]
+        L.fray_gpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.fray_gpu_host_unregister.argtypes = [C.c_void_p]
         L.fray_gpu_resolve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.fray_gpu_resolve_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.fray_gpu_frame_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_char_p]
@@ -260,6 +263,12 @@ class GpuContext:
         frame = make_frame(**frame_kw)
         self._check(self._lib.fray_gpu_render_device(self._ctx, C.byref(frame), d_rgb, stream), "fray_gpu_render_device")
 
+    def render_to_host(self, pinned_host: int, stream: int = 0, **frame_kw):
+        """Render this share (bucket_rank / bucket_count) and store the finished pixels of its own tiles straight into the
+        page-locked host frame at `pinned_host` (fray_gpu_render_to_host); asynchronous, wait with sync()."""
+        frame = make_frame(**frame_kw)
+        self._check(self._lib.fray_gpu_render_to_host(self._ctx, C.byref(frame), pinned_host, stream), "fray_gpu_render_to_host")
+
     def resolve_device(self, d_sum: int, d_rgb: int, spp: int, stream: int = 0):
         self._check(self._lib.fray_gpu_resolve_device(self._ctx, d_sum, d_rgb, spp, stream), "fray_gpu_resolve_device")
 
@@ -331,6 +340,16 @@ class MultiGpuContext:
         if rc != 0:
             raise FrayError(f"fray_gpu_multi_render failed ({rc}): {self._lib.fray_gpu_last_error().decode(errors='replace')}")
         return out, RenderStats.of(stats)
+
+
+def host_register(address: int, nbytes: int):
+    """Page-lock foreign host memory (a shared-memory mapping ...) so that kernels can store into it (fray_gpu_host_register)."""
+    if gpu_lib().fray_gpu_host_register(address, nbytes) != 0:
+        raise FrayError("fray_gpu_host_register: " + gpu_lib().fray_gpu_last_error().decode())
+
+
+def host_unregister(address: int):
+    gpu_lib().fray_gpu_host_unregister(address)
 
 
 def measure_peaks(device: int = 0, ms: float = 20.0) -> tuple[float, float]:

@@ -102,6 +102,19 @@ __global__ void combineKernel(const RenderParams p)
 	}
 }
 
+// the pixels of the owned tiles, device frame -> (mapped host) frame: fray_gpu_render_to_host for the wavefront path, whose passes
+// read the frame back while they build it
+__global__ void gatherOwnedKernel(const RenderParams p, const float* __restrict__ src)
+{
+	const unsigned slots = (unsigned) p.numOwnedTiles * 32u;
+	for (unsigned slot = blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += gridDim.x * blockDim.x) {
+		int px, py;
+		if (!slotPixel(p, slot, px, py)) continue;
+		const size_t i = 3 * ((size_t) py * p.width + px);
+		p.out[i] = src[i]; p.out[i + 1] = src[i + 1]; p.out[i + 2] = src[i + 2];
+	}
+}
+
 // ---- roofline denominators ---------------------------------------------------------------------------
 __global__ void ffmaPeakKernel(float* sink, int iters, float a, float b)
 {
@@ -639,6 +652,54 @@ int fray_gpu_resolve_to_host(FrayGpuCtx* c, const void* d_sum, float* pinned_rgb
 	cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : c->stream;
 	resolveKernel<<<c->numSMs * 4, 256, 0, st>>>((const float*) d_sum, dev, n, (float) spp);
 	CUDA_TRY(cudaGetLastError());
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_render_to_host(FrayGpuCtx* c, const FrayGpuFrame* frame, float* pinned_rgb, void* cuda_stream)
+{
+	if (!c || !frame || !pinned_rgb) return fail(FRAY_GPU_EINVAL, "null argument");
+	if (frame->flags & FRAY_FRAME_SUM) return fail(FRAY_GPU_EINVAL, "fray_gpu_render_to_host delivers finished pixels, not sums");
+	CUDA_TRY(cudaSetDevice(c->device));
+	float* dev = mappedHostPointer(pinned_rgb);
+	if (!dev) return fail(FRAY_GPU_EINVAL, "fray_gpu_render_to_host needs page-locked (pinned) host memory");
+	cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : c->stream;
+	FrayGpuFrame f = *frame;
+	f.flags |= FRAY_FRAME_OWNED_ONLY;
+	if (!waveEligible(c, &f)) return renderInto(c, &f, dev, st, true); // the kernels' own final stores go over PCIe
+	// wavefront frames are built up in device memory (the shadow pass adds to what the shade pass stored): copy the owned tiles out
+	int rc = renderInto(c, &f, c->dFrame, st, true);
+	if (rc != FRAY_GPU_OK) return rc;
+	rc = waveFinish(c); // a full queue means the frame is rendered again before it leaves
+	if (rc != FRAY_GPU_OK) return rc;
+	const int bcount = f.bucket_count > 0 ? f.bucket_count : 1, brank = f.bucket_count > 0 ? f.bucket_rank : 0;
+	const int tilesX = (c->width + FRAY_TILE_W - 1) / FRAY_TILE_W, tilesY = (c->height + FRAY_TILE_H - 1) / FRAY_TILE_H;
+	const int totalTiles = tilesX * tilesY;
+	RenderParams p;
+	memset(&p, 0, sizeof(p));
+	p.width = c->width; p.height = c->height;
+	p.tilesX = tilesX;
+	p.invTilesX = 1.0f / (float) tilesX;
+	p.exactDiv = (double) totalTiles >= 4e6 ? 1 : 0;
+	p.numOwnedTiles = totalTiles > brank ? (totalTiles - brank + bcount - 1) / bcount : 0;
+	p.taskStride = bcount;
+	p.taskOffset = brank;
+	p.out = dev;
+	gatherOwnedKernel<<<c->numSMs * 4, 256, 0, st>>>(p, c->dFrame);
+	CUDA_TRY(cudaGetLastError());
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_host_register(void* host, size_t bytes)
+{
+	if (!host || !bytes) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+	return FRAY_GPU_OK;
+}
+
+int fray_gpu_host_unregister(void* host)
+{
+	if (!host) return fail(FRAY_GPU_EINVAL, "null argument");
+	CUDA_TRY(cudaHostUnregister(host));
 	return FRAY_GPU_OK;
 }
 

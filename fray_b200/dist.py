@@ -19,6 +19,15 @@ static and needs exactly one collective at the end of the frame:
                  cannot start frame k+2 before the all-reduce of frame k+1, which rank 0 enters only after that copy (stream
                  order). Falls back to ``tiles`` where peer mapping is unavailable.
 
+* ``host``    -- the tile split when the frame is wanted in HOST memory (``render()``): the frame lives in a POSIX
+                 shared-memory mapping that every rank process maps and page-locks (fray_gpu_host_register), and every rank's
+                 GPU stores the finished pixels of its own tiles straight into it over its own PCIe link
+                 (fray_gpu_render_to_host). No partial frames, no reduce, no 1.9 MB device-to-host copy through one link; the
+                 only exchange is a pair of counters per rank in the same mapping ("share k is in memory" / "rank 0 has
+                 entered frame k"). Two frames are used alternately, as in ``p2p``. Bit-identical to the single-GPU frame
+                 whenever the tile split is. ``render_device()`` (a frame in rank 0's DEVICE memory) runs the ``samples`` or
+                 ``tiles`` reduction in this mode.
+
 The scene is replicated (the largest bundled scene is ~25 MB). There is no collective inside the render path.
 """
 from __future__ import annotations
@@ -86,6 +95,12 @@ class DistributedRenderer:
             self.mode = "tiles"
         if self.mode == "p2p" and self.world == 1:
             self.mode = "tiles"
+        self.device_mode = self.mode  # what render_device() does
+        self.shm = None
+        if self.mode == "host":
+            self.device_mode = choose_mode(self.spp, self.world)
+            if self.world == 1 or not self._setup_host():
+                self.mode = self.device_mode
         if self.mode != "p2p":
             self.partial = torch.zeros(self.shape, dtype=torch.float32, device=f"cuda:{self.device}")
             self.frame = torch.zeros_like(self.partial) if self.rank == 0 else None
@@ -125,6 +140,95 @@ class DistributedRenderer:
             self.frame = self.frame_pair[0]
         return True
 
+    # ---- ``host`` mode: one frame in shared, page-locked host memory ---------------------------------------------------------
+    _HOST_HEADER = 4096  # bytes in front of the two frames: per rank one 64-byte line {done, entered}
+
+    def _setup_host(self) -> bool:
+        """Rank 0 creates the mapping, everyone maps and page-locks it. Collective: all ranks succeed or fall back together."""
+        import mmap
+        torch, dist = self.torch, self.dist
+        nbytes = self._HOST_HEADER + 2 * self.shape[0] * self.shape[1] * self.shape[2] * 4
+        name = [None]
+        if self.rank == 0:
+            name[0] = f"/dev/shm/fray_frame_{os.getpid()}_{os.environ.get('MASTER_PORT', '0')}"
+            with open(name[0], "wb") as f:
+                f.truncate(nbytes)
+        dist.broadcast_object_list(name, src=0)
+        ok = 1
+        try:
+            fd = os.open(name[0], os.O_RDWR)
+            try:
+                self.shm = mmap.mmap(fd, nbytes)
+            finally:
+                os.close(fd)
+            self.shm_np = np.frombuffer(self.shm, dtype=np.uint8)
+            self.shm_addr = self.shm_np.ctypes.data
+            fb.host_register(self.shm_addr, nbytes)
+        except (OSError, ValueError, fb.FrayError) as e:
+            import sys
+            print(f"fray_b200.dist: rank {self.rank}: no shared host frame ({e}); falling back to the {self.device_mode} reduction", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{self.device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = int(flag.item())  # (waits for the collective: every rank is past its open() now)
+        if self.rank == 0:
+            os.unlink(name[0])  # every rank has it open (or has given up): the name can go
+        if all_ok == 0:
+            self._close_host()
+            return False
+        self.shm_flags = self.shm_np[:self._HOST_HEADER].view(np.int64).reshape(-1, 8)  # [rank] = {done, entered, ...}
+        n = self.shape[0] * self.shape[1] * self.shape[2]
+        self.shm_frames = self.shm_np[self._HOST_HEADER:].view(np.float32).reshape((2,) + self.shape)
+        self.shm_frame_bytes = n * 4
+        self.host_frames = 0
+        return True
+
+    def _close_host(self):
+        if self.shm is not None:
+            try:
+                fb.host_unregister(self.shm_addr)
+            except Exception:
+                pass
+            self.shm_flags = self.shm_frames = self.shm_np = None
+            try:
+                self.shm.close()
+            except BufferError:
+                pass  # a caller still holds a view of the last frame
+            self.shm = None
+
+    def _render_host(self, seed: int):
+        """Frame k goes to buffer k % 2. A rank may start frame k only after rank 0 has ENTERED frame k (rank 0's caller is then
+        done with frame k - 2, whose buffer this is); rank 0 returns frame k once every rank has reported its share in memory."""
+        import time
+        dbg = os.environ.get("FRAY_DIST_DEBUG")
+        t0 = time.perf_counter()
+        k = self.host_frames = self.host_frames + 1
+        flags = self.shm_flags
+        if self.rank == 0:
+            flags[0, 1] = k
+        else:
+            while flags[0, 1] < k:
+                pass
+        which = k & 1
+        stream = self.torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
+        t1 = time.perf_counter()
+        self.ctx.render_to_host(self.shm_addr + self._HOST_HEADER + which * self.shm_frame_bytes, stream, spp=self.spp, seed=seed,
+                                bucket_rank=self.rank, bucket_count=self.world)
+        t2 = time.perf_counter()
+        self.torch.cuda.current_stream().synchronize()  # this share is in host memory
+        t3 = time.perf_counter()
+        flags[self.rank, 0] = k
+        if self.rank != 0:
+            return None
+        for r in range(1, self.world):
+            while flags[r, 0] < k:
+                pass
+        t4 = time.perf_counter()
+        if dbg:
+            self.dbg = getattr(self, "dbg", [])
+            self.dbg.append(((t1 - t0) * 1e6, (t2 - t1) * 1e6, (t3 - t2) * 1e6, (t4 - t3) * 1e6))
+        return self.shm_frames[which]
+
     def _wrap_device_pointer(self, ptr: int, count: int):
         """A float32 torch tensor over `count` floats of device memory owned by the context (no copy)."""
         torch = self.torch
@@ -138,7 +242,8 @@ class DistributedRenderer:
         torch = self.torch
         # torch's default stream has handle 0, which the C ABI reads as "the context's own stream": name it explicitly
         stream = torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
-        if self.mode == "p2p":
+        mode = self.device_mode if self.mode == "host" else self.mode
+        if mode == "p2p":
             which = self.frames_rendered & 1  # double buffering: see the module docstring
             self.frames_rendered += 1
             target = self.peer_frame + which * self.shape[0] * self.shape[1] * self.shape[2] * 4
@@ -148,7 +253,7 @@ class DistributedRenderer:
             if self.rank == 0:
                 self.frame = self.frame_pair[which]
             return
-        kw = shard(self.rank, self.world, self.spp, self.mode)
+        kw = shard(self.rank, self.world, self.spp, mode)
         self.ctx.render_device(self.partial.data_ptr(), stream, spp=self.spp, seed=seed, flags=fb.FRAME_SUM, **kw)
         if self.world > 1:
             self.dist.reduce(self.partial, dst=0, op=self.dist.ReduceOp.SUM)
@@ -158,6 +263,8 @@ class DistributedRenderer:
     def render(self, seed: int = 42) -> np.ndarray | None:
         """End to end: render, exchange, and bring the frame to (pinned) host memory on rank 0. With a reduction, rank 0's
         resolve pass stores the quotients straight into the pinned frame (fray_gpu_resolve_to_host): no device-to-host copy."""
+        if self.mode == "host":
+            return self._render_host(seed)
         if self.mode == "p2p":
             self.render_device(seed)
             if self.rank != 0:
@@ -186,4 +293,7 @@ class DistributedRenderer:
             self.ctx.frame_close(self.peer_frame)
             self.peer_frame = 0
         self.frame = None
+        if self.mode == "host":
+            self.torch.cuda.synchronize()
+            self._close_host()
         self.ctx.close()

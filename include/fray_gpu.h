@@ -331,6 +331,21 @@ int fray_gpu_resolve_device(FrayGpuCtx* ctx, const void* d_sum, void* d_rgb, int
  * device-to-host copy follows. Asynchronous on `cuda_stream`; FRAY_GPU_EINVAL for pageable memory. */
 int fray_gpu_resolve_to_host(FrayGpuCtx* ctx, const void* d_sum, float* pinned_rgb, int32_t spp, void* cuda_stream);
 
+/* Tile split with the frame wanted in HOST memory: renders the share `frame` describes (bucket_rank / bucket_count; all
+ * samples) and stores the finished pixels of ITS OWN tiles -- nothing else -- into the page-locked host frame `pinned_rgb`
+ * (width*height*3 floats), asynchronously on `cuda_stream`. Every GPU sends its tiles over its own PCIe link; the shares of N
+ * GPUs -- N threads of one process, or N rank processes that map one shared-memory frame and page-lock it with
+ * fray_gpu_host_register() -- assemble the frame without a reduction, a peer copy or a device-to-host copy of the whole frame.
+ * (This is what every worker thread of the reference does with its buckets and the shared `vfb`, src/main.cpp:331-370.) The
+ * caller waits for all shares (fray_gpu_sync on each) before it reads the frame. FRAY_GPU_EINVAL for pageable memory. */
+int fray_gpu_render_to_host(FrayGpuCtx* ctx, const FrayGpuFrame* frame, float* pinned_rgb, void* cuda_stream);
+
+/* Page-lock `bytes` of host memory that something else allocated (a POSIX shared-memory mapping, a memory-mapped file, a
+ * buffer of the host application) and map it into the CUDA address space, so that kernels can store into it
+ * (fray_gpu_render_to_host, fray_gpu_resolve_to_host). Undo with fray_gpu_host_unregister() before the memory is unmapped. */
+int fray_gpu_host_register(void* host, size_t bytes);
+int fray_gpu_host_unregister(void* host);
+
 /* Wait for the context's outstanding work and fetch the statistics of the last render. */
 int fray_gpu_sync(FrayGpuCtx* ctx, FrayGpuStats* stats);
 

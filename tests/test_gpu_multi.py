@@ -116,3 +116,47 @@ def test_cli_devices_and_prepass(tmp_path, data_dir):
     np.testing.assert_allclose(got, np.floor(np.clip(want, 0, 1) * np.float32(255) + np.float32(0.5)) / 255, atol=1e-6)
     pre = fb.load_image(str(tmp_path / "frame.prepass.bmp"))
     assert pre.shape == got.shape and (pre[:16, :16] == pre[0, 0]).all()
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "boxed", "forest_aa"])
+def test_shares_gathered_straight_into_shared_host_memory(name, golden_cases, data_dir):
+    """fray_gpu_render_to_host + fray_gpu_host_register (the `host` mode of fray_b200/dist.py): three shares of a tile split
+    store their own tiles into one page-locked frame that lives in a shared-memory mapping -- the frame a single render call
+    produces, pixel for pixel within FP32 regrouping (a share may cut a pixel's samples into other chunks), every pixel
+    written exactly once. Path-traced (the kernels' own final stores go over PCIe) and wavefront (owned tiles copied out)."""
+    import mmap
+    path, seed = golden_scene(golden_cases, name)
+    sc = fb.Scene(path)
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    want, ws = ctx.render(seed=seed)
+    nbytes = sc.height * sc.width * 3 * 4
+    shm = mmap.mmap(-1, nbytes)  # anonymous shared mapping: what N rank processes would map by name
+    view = np.frombuffer(shm, dtype=np.float32).reshape(sc.height, sc.width, 3)
+    addr = view.ctypes.data
+    fb.host_register(addr, nbytes)
+    try:
+        view[:] = np.nan
+        rays = 0
+        for rank in range(3):
+            ctx.render_to_host(addr, 0, seed=seed, bucket_rank=rank, bucket_count=3)
+            rays += ctx.sync().rays
+            assert np.isnan(view).any() == (rank < 2)  # pixels of the other shares are not touched
+        np.testing.assert_allclose(view, want, rtol=2e-6, atol=1e-7)
+        assert rays == ws.rays
+        with pytest.raises(fb.FrayError):
+            ctx.render_to_host(addr, 0, seed=seed, flags=fb.FRAME_SUM)
+    finally:
+        fb.host_unregister(addr)
+        ctx.close()
+        del view
+        shm.close()
+
+
+def test_render_to_host_rejects_pageable_memory(golden_cases, data_dir):
+    path, seed = golden_scene(golden_cases, "cornell_box")
+    sc = fb.Scene(path)
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    out = np.zeros((sc.height, sc.width, 3), np.float32)
+    with pytest.raises(fb.FrayError):
+        ctx.render_to_host(out.ctypes.data, 0, seed=seed)
+    ctx.close()
