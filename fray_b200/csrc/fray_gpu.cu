@@ -70,7 +70,7 @@ struct FrayGpuCtx {
 	FrayGpuFrame lastFrame = {};
 	float* lastOut = nullptr;
 	bool lastTimed = false;
-	int forceChunk = 0;             // > 0: samples per work item imposed by fray_gpu_multi_render (bit-identical tile shares)
+	double chunkPixels = 0;         // > 0: cut the samples into the chunks a frame of this many pixels gets (fray_gpu_multi_render: bit-identical tile shares)
 	int waveFan = 1;                // secondary rays one hit can spawn (glossy samples), for the first guess of the queue size
 	bool waveSecondary = false;     // some node's shader reflects or refracts: the ray tree is deeper than the camera rays
 	int waveLitPerRay = 1;          // Lambert / Phong evaluations one hit can ask for (through Layered shaders)
@@ -306,14 +306,31 @@ static int pow2Floor(int v)
 }
 
 // samples per work item (render_kernels.cuh) for a call that owns `ownedTiles` tiles and renders `samples` samples of each pixel
-static int chooseChunk(int ownedTiles, int samples, int gridBlocks)
+// How the samples [0, samples) of a pixel are cut into chunks (render_kernels.cuh: a work item is one chunk of one pixel, and the
+// queue hands out all items of chunk 0 first). Guided self-scheduling: one chunk index gives every lane pixels / lanes items,
+// and a chunk is a third of the paths a lane still has to do -- at most 8 (beyond that the bookkeeping per item and the chunk
+// sums are noise already), at least 1 -- so most of the frame runs in items of 8 paths and the queue ends in items of one: the
+// lanes run dry within one path (~35 us on a busy SM) of each other, where uniform chunks of 8 drained for up to eight.
+// One GPU, the headline frame (160000 pixels, 256 paths, 132608 lanes): 8 x 30, 6, 4, 2, 1, 1, 1, 1 = 37 chunks; an eighth of
+// its samples: 8, 8, 6, 4, 2, 1, 1, 1, 1 = 9 chunks where uniform chunks of 1 needed 32 (a quarter of the chunk sums to write
+// and add). `starts` gets numChunks + 1 entries. When that makes more than FRAY_MAX_CHUNKS chunks, or more than 192 MB of chunk
+// sums (one RGB triple per pixel and chunk), all sizes are doubled until it does not (smallpt, 1024 paths: 32 ... 24, 4, 4).
+static void buildChunks(double pixels, int samples, double lanes, std::vector<int>& starts)
 {
-	const double samplesPerLane = (double) ownedTiles * 32.0 * samples / ((double) gridBlocks * 128.0);
-	int C = pow2Floor(std::max(1, (int) (samplesPerLane / 32.0)));
-	const double maxChunks = std::max(1.0, 192e6 / ((double) std::max(ownedTiles, 1) * 32.0 * 12.0));
-	C = std::max(C, (int) ((samples + maxChunks - 1) / maxChunks));
-	if (const char* e = getenv("FRAY_GPU_CHUNK")) C = std::max(1, atoi(e)); // experiments only
-	return std::min(C, samples);
+	const double perLane = std::max(pixels, 1.0) / std::max(lanes, 1.0);
+	const int maxChunks = (int) std::min((double) FRAY_MAX_CHUNKS, std::max(1.0, 192e6 / (std::max(pixels, 1.0) * 12.0)));
+	const char* e = getenv("FRAY_GPU_CHUNK"); // experiments only: uniform chunks of that many samples
+	const int uniform = e ? std::max(1, atoi(e)) : 0;
+	for (int unit = 1;; unit *= 2) {
+		starts.assign(1, 0);
+		for (int done = 0; done < samples;) {
+			const int left = samples - done;
+			int len = unit * std::max(1, std::min(8, (int) (left * perLane / (3.0 * unit))));
+			if (uniform) len = uniform * unit;
+			starts.push_back(done += std::min(left, len));
+		}
+		if ((int) starts.size() - 1 <= maxChunks || unit >= samples) return;
+	}
 }
 
 // ---- wavefront Whitted path ------------------------------------------------------------------------------------------------
@@ -479,17 +496,22 @@ static int renderInto(FrayGpuCtx* c, const FrayGpuFrame* f, float* dOut, cudaStr
 	// share a frame. Measured on a 1/8 share of the headline frame (tools/share_time.py, 1.10 ms of work): C = 1 1.229 ms,
 	// C = 2 1.204 ms, C = 4 1.233 ms, C = 8 1.289 ms. The scratch buffer (one RGB sum per pixel and chunk) is kept below 192 MB
 	const int samples = std::max(1, s1 - s0);
-	int C = chooseChunk(ownedTiles, samples, cfg.gridBlocks);
-	if (c->forceChunk > 0) C = std::min(c->forceChunk, samples);
-	p.chunk = C;
-	p.numChunks = (samples + C - 1) / C;
+	std::vector<int> starts;
+	buildChunks(c->chunkPixels > 0 ? c->chunkPixels : (double) ownedTiles * 32.0, samples, (double) cfg.gridBlocks * 128.0, starts);
+	p.numChunks = (int) starts.size() - 1;
+	for (int k = 0; k <= p.numChunks; k++) p.chunkStart[k] = (unsigned) starts[k];
+	p.numBulk = 1; // the leading run of equally long chunks goes tile by tile, the descending rest chunk by chunk
+	while (p.numBulk < p.numChunks && starts[p.numBulk + 1] - starts[p.numBulk] == starts[1] - starts[0]) p.numBulk++;
+	if (p.numBulk == p.numChunks && p.numChunks > 1) p.numBulk--; // (uniform chunks: keep the decode of the rest in use)
+	p.bulkItems = (unsigned) p.numBulk * (unsigned) ownedTiles * 32u;
+	p.invNumBulk = 1.0f / (float) p.numBulk;
 	p.tilesX = tilesX;
 	p.numOwnedTiles = ownedTiles;
 	p.taskStride = bcount;
 	p.taskOffset = brank;
 	p.totalItems = (unsigned) ownedTiles * 32u * (unsigned) p.numChunks;
 	p.invTilesX = 1.0f / (float) tilesX;
-	p.invNumChunks = 1.0f / (float) p.numChunks;
+	p.invNumOwnedTiles = 1.0f / (float) std::max(ownedTiles, 1);
 	p.exactDiv = ((double) totalTiles >= 4e6 || (double) ownedTiles * p.numChunks >= 4e6) ? 1 : 0; // beyond 2^22: integer division
 	p.out = dOut;
 	p.counters = c->dCounters;
@@ -1024,16 +1046,11 @@ int fray_gpu_multi_render(FrayGpuMulti* mg, const FrayGpuFrame* frame, int split
 	const size_t frameFloats = (size_t) mg->width * mg->height * 3;
 	CUDA_TRY(cudaSetDevice(c0->device));
 	if (split == FRAY_GPU_SPLIT_SAMPLES && !mg->dPartials) CUDA_TRY(cudaMalloc(&mg->dPartials, frameFloats * sizeof(float) * n));
-	// tile shares with the samples-per-item of the whole frame on one GPU: every pixel is then summed exactly as there
-	int chunk = 0;
+	// tile shares with the chunks of the whole frame on one GPU: every pixel is then summed exactly as there
+	double chunkPixels = 0;
 	if (split == FRAY_GPU_SPLIT_TILES && n > 1 && frame->mode == FRAY_RENDER_BEAUTY && !(frame->flags & FRAY_GPU_MULTI_FAST)) {
-		int& occ = gi ? c0->occGI : c0->occWhitted;
-		if (occ < 0) {
-			occ = c0->precision == FRAY_GPU_FP32 ? renderOccupancy<float>(c0->sc32, c0->features, gi) : renderOccupancy<double>(c0->sc64, c0->features, gi);
-			if (occ < 1) occ = 1;
-		}
 		const int tilesX = (mg->width + FRAY_TILE_W - 1) / FRAY_TILE_W, tilesY = (mg->height + FRAY_TILE_H - 1) / FRAY_TILE_H;
-		chunk = chooseChunk(tilesX * tilesY, spp, c0->numSMs * occ);
+		chunkPixels = (double) tilesX * tilesY * 32.0;
 	}
 	for (int d = 0; d < n; d++) {
 		FrayGpuFrame f = *frame;
@@ -1051,7 +1068,7 @@ int fray_gpu_multi_render(FrayGpuMulti* mg, const FrayGpuFrame* frame, int split
 			mg->outs[d] = mg->dPartials + (size_t) d * frameFloats;
 		}
 		mg->frames[d] = f;
-		mg->ctx[d]->forceChunk = chunk;
+		mg->ctx[d]->chunkPixels = chunkPixels;
 	}
 	{
 		std::lock_guard<std::mutex> lk(mg->m);
@@ -1093,7 +1110,7 @@ int fray_gpu_multi_render(FrayGpuMulti* mg, const FrayGpuFrame* frame, int split
 		std::unique_lock<std::mutex> lk(mg->m);
 		mg->cvDone.wait(lk, [&] { return mg->finished == n; });
 	}
-	for (int d = 0; d < n; d++) mg->ctx[d]->forceChunk = 0;
+	for (int d = 0; d < n; d++) mg->ctx[d]->chunkPixels = 0;
 	for (int d = 0; d < n && rc == FRAY_GPU_OK; d++)
 		if (mg->rcs[d] != FRAY_GPU_OK) rc = fail(mg->rcs[d], "share " + std::to_string(d) + ": " + mg->errs[d]);
 	if (rc == FRAY_GPU_OK && stats) {

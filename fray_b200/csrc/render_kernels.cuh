@@ -3,8 +3,13 @@
 // Scheduling model ("persistent lanes, two-level work queue, path regeneration"):
 //   * the frame is cut into 8x4 pixel tiles (row-major over the image); a call owns the tiles t with
 //     t % taskStride == taskOffset (multi-GPU tile split) and a sample range [s0, s1) of every owned pixel (sample split);
-//   * the samples of a pixel are cut into CHUNKS of C consecutive samples. A WORK ITEM is (owned pixel, chunk); item ids are
-//     laid out so that 32 consecutive ids are the 32 pixels of one tile for one chunk (coherent primary rays);
+//   * the samples of a pixel are cut into CHUNKS of consecutive samples. A WORK ITEM is (owned pixel, chunk); item ids are
+//     laid out so that 32 consecutive ids are the 32 pixels of one tile for one chunk (coherent primary rays). Chunk sizes
+//     DESCEND (guided self-scheduling, fray_gpu.cu: buildChunks): most of the frame runs in items of 8 paths -- little
+//     bookkeeping, few chunk sums -- and the queue ends in items of one path, so that the lanes run dry within one path of each
+//     other (~35 us), not one item. The leading chunks of equal size (the "bulk") are handed out tile by tile, all chunks of a
+//     tile in a row -- what runs at any one time covers a small part of the screen, which the textures and meshes of zaphod
+//     want (1.40 ms against 1.47 ms chunk by chunk) -- and the descending rest chunk by chunk, the smallest last;
 //   * persistent CTAs (grid = SMs x resident CTAs). Every LANE owns one item at a time and is a state machine: whenever
 //     its path (GI) or ray tree (Whitted) is finished it starts the next sample of its item, and when the item is used up it
 //     writes the chunk's sum and takes the next item. Items come from a warp-level pool (a contiguous id range in uniform
@@ -26,6 +31,7 @@ namespace fray {
 #define FRAY_TILE_W 8
 #define FRAY_TILE_H 4
 #define FRAY_POOL_BATCH 32 // item ids fetched per atomic
+#define FRAY_MAX_CHUNKS 96  // chunks per pixel (entries of RenderParams::chunkStart)
 
 struct RenderParams {
 	int width, height;
@@ -34,14 +40,17 @@ struct RenderParams {
 	uint32_t seed;
 	uint32_t roundKeys[10]; // philoxRoundKeys(seed)
 	int sumOnly;      // FRAY_FRAME_SUM
-	int chunk;        // C: samples per work item
-	int numChunks;    // ceil((s1 - s0) / C)
+	int numChunks;    // chunks the sample range of a pixel is cut into
+	int numBulk;      // the leading chunks of equal size, handed out tile by tile; the rest chunk by chunk (see below)
+	unsigned int bulkItems; // numBulk * numOwnedTiles * 32
+	float invNumBulk;
+	unsigned chunkStart[FRAY_MAX_CHUNKS + 1]; // chunk k = samples s0 + [chunkStart[k], chunkStart[k + 1]) (descending sizes, see the head of this file)
 	int tilesX;       // tiles per image row
-	float invTilesX, invNumChunks; // reciprocals for divmodSmall
+	float invTilesX, invNumOwnedTiles; // reciprocals for divmodSmall
 	int exactDiv;     // ranges too large for the float estimate: use integer division
 	int numOwnedTiles;
 	int taskStride, taskOffset; // owned tile j is tile j * taskStride + taskOffset of the frame
-	unsigned int totalItems;    // numOwnedTiles * 32 * numChunks
+	unsigned int totalItems;    // numChunks * numOwnedTiles * 32
 	float* out;       // [height][width][3]
 	float* scratch;   // numChunks > 1: [chunk][owned pixel slot][3]
 	unsigned long long* counters; // rays, primary, shadow
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const unsigned ltMask = (1u << lane) - 1u;
 	__shared__ uint2 stagedItem[4][32]; // per warp, the decoded items of its pool batch: {px | py << 16 (all ones: outside the image), output index}
-	__shared__ int stagedCur[4];        // first sample of the batch's chunk
+	__shared__ int stagedCur[4], stagedEnd[4]; // the samples of the batch's chunk
 	const bool randomOffsets = sc.cam.dof || sc.gi;
 	const bool stereo = (F & FRAY_F_LENS) && sc.cam.stereoSep > 0;
 
@@ -177,10 +186,15 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 				if (base >= p.totalItems) { exhausted = true; break; }
 				poolNext = base;
 				poolEnd = base + (unsigned) FRAY_POOL_BATCH; // totalItems is a multiple of the batch
-				// The batch is one (owned tile, chunk) pair: id = (ownedTile * numChunks + chunk) * 32 + within. Every lane decodes
+				// The batch is one (chunk, owned tile) pair: id = (chunk * numOwnedTiles + ownedTile) * 32 + within. Every lane decodes
 				// item base + lane, once per 32 items and with all lanes busy, and parks it in shared memory for whoever takes it.
 				unsigned chunk, j;
-				divmodSmall(base >> 5, (unsigned) p.numChunks, p.invNumChunks, p.exactDiv != 0, j, chunk);
+				if (base < p.bulkItems) { // bulk: id = (ownedTile * numBulk + chunk) * 32 + within
+					divmodSmall(base >> 5, (unsigned) p.numBulk, p.invNumBulk, p.exactDiv != 0, j, chunk);
+				} else {                  // rest: id = bulkItems + ((chunk - numBulk) * numOwnedTiles + ownedTile) * 32 + within
+					divmodSmall((base - p.bulkItems) >> 5, (unsigned) p.numOwnedTiles, p.invNumOwnedTiles, p.exactDiv != 0, chunk, j);
+					chunk += (unsigned) p.numBulk;
+				}
 				const unsigned slot = (j << 5) | lane;
 				int qx, qy;
 				uint2 st;
@@ -188,7 +202,10 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 				st.y = p.numChunks == 1 ? (unsigned) (qy * p.width + qx) : chunk * ((unsigned) p.numOwnedTiles * 32u) + slot;
 				__syncwarp();
 				stagedItem[warp][lane] = st;
-				if (lane == 0) stagedCur[warp] = p.s0 + (int) chunk * p.chunk;
+				if (lane == 0) {
+					stagedCur[warp] = p.s0 + (int) p.chunkStart[chunk];
+					stagedEnd[warp] = p.s0 + (int) p.chunkStart[chunk + 1];
+				}
 				__syncwarp();
 			}
 			const unsigned avail = poolEnd - poolNext;
@@ -200,7 +217,7 @@ __global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F
 					px = (int) (st.x & 0xffffu);
 					py = (int) (st.x >> 16);
 					cur = stagedCur[warp];
-					end = min(cur + p.chunk, p.s1);
+					end = stagedEnd[warp];
 					accum = Col(0, 0, 0);
 					outIndex = st.y;
 				}
