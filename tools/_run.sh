@@ -1,14 +1,6 @@
-set -x
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02k_bench_1gpu.json 2> gpurun_out/r02k_bench_1gpu.err; tail -c 600 gpurun_out/r02k_bench_1gpu.json
-python tools/time_configs.py --fp32 > gpurun_out/r02k_all_configs_timing.log 2>&1
-python tools/share_time.py --world 8 --chunks 0,1,2 > gpurun_out/r02k_share_times.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:renderKernel -s 3 -c 1 -f -o gpurun_out/r02k_cornell256 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-configs > gpurun_out/ncu_x.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02k_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-configs > gpurun_out/ncu_x.log 2>&1
-for k in waveTraceKernel waveShadeKernel waveShadowKernel; do
-ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/r02k_forest_$k python tools/render_once.py forest frameWidth=3840 frameHeight=2160 --frames 2 > gpurun_out/ncu_x.log 2>&1
+for sp in samples auto tiles; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 5 --split $sp --no-other-configs > gpurun_out/r02m_bench_4gpu_$sp.json 2> gpurun_out/r02m_bench_4gpu_$sp.err; cat gpurun_out/r02m_bench_4gpu_$sp.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$sp', 'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'], d['config']['split'], d.get('multi_gpu_check',{}).get('max_abs_diff'))"
 done
-ncu --set full --clock-control none --import-source on -k regex:waveShadowKernel -s 1 -c 1 -f -o gpurun_out/r02k_boxed_waveShadowKernel python tools/render_once.py boxed --frames 2 > gpurun_out/ncu_x.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:waveTraceKernel -s 6 -c 1 -f -o gpurun_out/r02k_dragon_waveTraceKernel python tools/render_once.py hw9/dragon --frames 2 > gpurun_out/ncu_x.log 2>&1
-for sc in boxed hw9/dragon; do n=$(echo $sc | tr / _); ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02k_launches_$n.csv python tools/render_once.py $sc --frames 2 > /dev/null 2>&1; done
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02k_launches_forest4k.csv python tools/render_once.py forest frameWidth=3840 frameHeight=2160 --frames 2 > /dev/null 2>&1
-ls -la gpurun_out | tail -20
