@@ -426,7 +426,7 @@ static int renderWave(FrayGpuCtx* c, const RenderParams& rp, float* dOut, cudaSt
 	if (!w.direct) CUDA_TRY(cudaMemsetAsync(w.acc, 0, (size_t) c->width * c->height * 3 * sizeof(long long), stream));
 	cudaError_t e = launchWaveFrame(c->sc32, w, c->features, c->waveCfg);
 	if (e != cudaSuccess) return fail(FRAY_GPU_ECUDA, std::string("wavefront kernel launch: ") + cudaGetErrorString(e));
-	c->launches = c->waveCfg.waves * (c->sc32.numLights > 0 ? 3 : 2) + (w.direct ? 0 : 1);
+	c->launches = c->waveCfg.waves * ((c->sc32.numLights > 0 && !c->waveCfg.fused) ? 3 : 2) + (w.direct ? 0 : 1);
 	if (timed) CUDA_TRY(cudaEventRecord(c->evStop, stream));
 	c->pendingStats = timed;
 	c->lastStream = stream;

@@ -175,12 +175,15 @@ __device__ __forceinline__ void waveAccumulate(const WaveParams& p, int pixel, c
 	if (c.b != 0.0f) atomicAdd(a + 2, (unsigned long long) waveFixed(c.b));
 }
 
+#define FRAY_FUSED_LIT 2 // lit records a ray may park for the fused shade + shadow kernel (scenes whose shaders produce more use three passes)
+
 struct WaveSink {
 	const DScene<float>& sc;
 	const WaveParams& p;
 	unsigned litBase; // first lit-record slot of the ray being shaded
 	int litUsed;
 	Col known;        // direct frames: what SHADE knows of the ray's radiance, stored once by flush()
+	WaveLit* parked;  // fused kernel: the ray's lit records stay with the thread (nullptr: they go to the queue)
 	__device__ __forceinline__ void add(const WaveRay& r, const Col& c)
 	{
 		if (p.direct) known = known + c;
@@ -204,6 +207,7 @@ struct WaveSink {
 	__device__ __forceinline__ void lit(const WaveLit& L)
 	{
 		if (litUsed >= p.litPerRay) { p.ctr[FRAY_WCTR_OVERFLOW] = 2; return; } // cannot happen: litPerRay is the scene's maximum
+		if (parked) { parked[litUsed++] = L; return; }
 		const unsigned slot = litBase + (unsigned) litUsed++;
 		qst(p.litA + slot, make_float4(L.ip.x, L.ip.y, L.ip.z, __int_as_float(L.pixel)));
 		qst(p.litB + slot, make_float4(L.n.x, L.n.y, L.n.z, __uint_as_float(waveMeta(L.origin, 0, L.eye, L.phong))));
@@ -218,6 +222,7 @@ struct WaveSink {
 	__device__ __forceinline__ void begin(unsigned i) { litBase = i * (unsigned) p.litPerRay; litUsed = 0; known = Col(0, 0, 0); }
 	__device__ __forceinline__ void end()
 	{
+		if (parked) return;
 		for (int k = litUsed; k < p.litPerRay; k++) qst(p.litA + litBase + (unsigned) k, make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1)));
 	}
 };
@@ -340,14 +345,25 @@ __global__ void __launch_bounds__(128, FRAY_WAVE_TRACE_CTAS) waveTraceKernel(con
 }
 
 // ---- SHADE -----------------------------------------------------------------------------------------------------------------
-template <int F>
+// FUSED: scenes where a lit record means a shadow ray or two (point lights) and a ray produces at most FRAY_FUSED_LIT records.
+// The records never leave the thread: when the ray is shaded its light loops run right here (the very code of the shadow pass,
+// summed in the same order, delivered by the same operations: the frame is bit-identical to the three-pass frame) and there is
+// no shadow pass. At 3840x2160 forest's records are 0.93 GB of DRAM traffic per frame, written once to be read once -- and
+// that round trip turned out CHEAPER than running the walks inside the shade kernel (80 registers, 6 resident CTAs, 6400 + 2800
+// instructions): forest 4K 1.51 -> 1.66 ms, with AA 6.93 -> 7.51 ms, dragon 4.74 -> 4.78 ms. Kept as a measured alternative
+// (FRAY_GPU_FUSE=1); three passes are the default.
+template <int F, bool FUSED>
 __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc, const WaveParams p)
 {
 	const FlatTab ft = stageFlat<float, F>(sc);
 	__shared__ unsigned prefix[FRAY_WAVE_REGIONS + 1];
 	const unsigned n = waveRayCount(p, prefix);
 	const bool randomOffsets = sc.cam.dof || sc.gi;
-	WaveSink sink{ sc, p, 0u, 0, Col(0, 0, 0) };
+	WaveLit parkedLit[FUSED ? FRAY_FUSED_LIT : 1];
+	WaveSink sink{ sc, p, 0u, 0, Col(0, 0, 0), FUSED ? parkedLit : nullptr };
+	KdStackShared stk;
+	if constexpr (FUSED) stk = waveStack(p);
+	unsigned traced = 0;
 	unsigned primaries = 0;
 	WaveWork work;
 	work.init(p, 1, n);
@@ -373,14 +389,30 @@ __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc
 		waveShade<F>(sc, ft, r, wh, p.rp.roundKeys, p.rp.seed, count, sink);
 		sink.end();
 		sink.flush(r.pixel);
+		if constexpr (FUSED) {
+			if (sink.litUsed > 0) { // what waveShadowKernel does with the ray's records
+				Col sum(0, 0, 0);
+				for (int k = 0; k < sink.litUsed; k++)
+					sum = sum + waveEyeColor(sc, parkedLit[k].eye, waveLightLoop<F>(sc, ft, parkedLit[k], p.rp.roundKeys, p.rp.seed, stk, traced));
+				if (p.direct) waveAddDirect(p, r.pixel, sum);
+				else waveAccumulate(p, r.pixel, sum);
+			}
+		}
 		if (p.wave == 0 && stereo) { // the right eye goes on in the stream where the left eye's light loops stopped
 			right.count = count;
 			sink.ray(right);
 		}
 	}
-	unsigned long long total = primaries;
-	for (int m = 16; m > 0; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+	unsigned long long total = primaries, shadows = traced;
+	for (int m = 16; m > 0; m >>= 1) {
+		total += __shfl_xor_sync(0xffffffffu, total, m);
+		shadows += __shfl_xor_sync(0xffffffffu, shadows, m);
+	}
 	if ((threadIdx.x & 31u) == 0 && total) atomicAdd(p.rp.counters + 1, total);
+	if (FUSED && (threadIdx.x & 31u) == 0 && shadows) {
+		atomicAdd(p.rp.counters + 0, shadows);
+		atomicAdd(p.rp.counters + 2, shadows);
+	}
 }
 
 // ---- SHADOW ----------------------------------------------------------------------------------------------------------------
@@ -482,6 +514,7 @@ struct WaveLaunch {
 	int waves;          // waves to enqueue
 	cudaStream_t stream;
 	int occTrace, occShade, occShadow; // resident CTAs per SM (0: query)
+	bool fused;         // out: the light loops ran inside the shade pass (two launches per wave)
 };
 
 cudaError_t launchWaveFrame(const DScene<float>& sc, WaveParams p, int features, WaveLaunch& cfg);
@@ -492,13 +525,18 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 	const size_t flat = (F & FRAY_F_FLAT) ? ((flatSmemBytes(sc) + 15) & ~(size_t) 15) : 0;
 	const size_t stack = (size_t) FRAY_KD_SHORT * 128 * sizeof(uint2);
 	p.stackOffset = (unsigned) flat;
+	// shade + shadow in one kernel where a record means few shadow rays: OFF unless FRAY_GPU_FUSE=1 (measured, see waveShadeKernel)
+	static const bool fuse = getenv("FRAY_GPU_FUSE") != nullptr;
+	const bool fused = cfg.fused = fuse && sc.numLights > 0 && sc.lightSamples < FRAY_WAVE_SHADOW_MANY && p.litPerRay <= FRAY_FUSED_LIT;
 	if (cfg.occTrace <= 0) {
 		cudaFuncSetAttribute(waveTraceKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaFuncSetAttribute(waveShadowKernel<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaFuncSetAttribute(waveShadowKernel<F, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
-		cudaFuncSetAttribute(waveShadeKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) flat);
+		cudaFuncSetAttribute(waveShadeKernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) flat);
+		cudaFuncSetAttribute(waveShadeKernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occTrace, waveTraceKernel<F>, 128, flat + stack);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F>, 128, flat);
+		if (fused) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F, true>, 128, flat + stack);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F, false>, 128, flat);
 		if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 6>, 128, flat + stack);
 		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 8>, 128, flat + stack);
 		if (cfg.occTrace < 1 || cfg.occShade < 1 || cfg.occShadow < 1) return cudaErrorLaunchOutOfResources;
@@ -506,7 +544,11 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 	for (int w = 0; w < cfg.waves; w++) {
 		p.wave = w;
 		waveTraceKernel<F><<<cfg.numSMs * cfg.occTrace, 128, flat + stack, cfg.stream>>>(sc, p);
-		waveShadeKernel<F><<<cfg.numSMs * cfg.occShade, 128, flat, cfg.stream>>>(sc, p);
+		if (fused) {
+			waveShadeKernel<F, true><<<cfg.numSMs * cfg.occShade, 128, flat + stack, cfg.stream>>>(sc, p);
+			continue;
+		}
+		waveShadeKernel<F, false><<<cfg.numSMs * cfg.occShade, 128, flat, cfg.stream>>>(sc, p);
 		if (sc.numLights > 0) {
 			if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) waveShadowKernel<F, 6><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
 			else waveShadowKernel<F, 8><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
