@@ -43,6 +43,15 @@ def main():
         assert lib.fray_emul_render(scene.flat, C.byref(frame), out.ctypes.data, C.byref(stats), precision, 4) == 0
         assert kw.get("mode", fb.RENDER_BEAUTY) != fb.RENDER_BEAUTY or np.isfinite(out).all()  # a miss has distance inf in the AOV
 
+    lib.fray_emul_render_wave.argtypes = [C.c_void_p, C.POINTER(fb.FrayFrame), C.c_void_p, C.POINTER(fb.FrayStats), C.c_int]
+
+    def render_wave(scene, kd_short, **kw):
+        """the wavefront stages (wave.cuh: short-stack KD walk with leaf boxes, origin mask, light loop); -2: not a wavefront scene"""
+        out = np.empty((scene.height, scene.width, 3), np.float32)
+        frame, stats = fb.make_frame(**kw), fb.FrayStats()
+        rc = lib.fray_emul_render_wave(scene.flat, C.byref(frame), out.ctypes.data, C.byref(stats), kd_short)
+        assert rc in (0, -2) and (rc != 0 or np.isfinite(out).all())
+
     todo = [golden_scene(cases, name) for name in cases]
     extra = os.path.join(scenes.DATA_DIR, "flat_transforms__test.fray")
     shutil.copyfile(os.path.join(ROOT, "tests", "scenes", "flat_transforms.fray"), extra)
@@ -61,6 +70,8 @@ def main():
             render(sc, precision, seed=seed)
             render(sc, precision, mode=fb.RENDER_AOV)
             render(sc, precision, seed=seed, bucket_rank=1, bucket_count=3)
+        render_wave(sc, 0, seed=seed)
+        render_wave(sc, 2, seed=seed)  # a two-entry short stack: kd-restarts on every deep walk
         print("clean:", os.path.basename(path), flush=True)
     print("asan/ubsan: no findings")
 
