@@ -418,8 +418,12 @@ __global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc
 // ---- SHADOW ----------------------------------------------------------------------------------------------------------------
 // one thread per lit record: its whole light loop (wave.cuh, waveLightLoop), one term delivered to the pixel's accumulator.
 // Compiled for CTAS resident CTAs per SM: 8 (64 registers, ~260 bytes of spills inside the light loop) where a record means one
-// or two shadow rays and occupancy hides the record fetch, 6 (80 registers) where it means many (area lights: boxed 2.81 -> 2.51 ms,
-// while forest and dragon lose 2-3 % with it).
+// or two shadow rays and occupancy hides the record fetch from DRAM (forest and dragon lose 2-4 % with 6), and
+// FRAY_WAVE_SHADOW_HEAVY_CTAS = 3 (168 registers, nothing spilled) where it means many (area lights): 32 walks per record out of
+// the L1 are arithmetic and L1 latency, which twelve warps per SM cover, and every spilled value is reloaded 32 times.
+#ifndef FRAY_WAVE_SHADOW_HEAVY_CTAS
+#define FRAY_WAVE_SHADOW_HEAVY_CTAS 3 // resident CTAs per SM the shadow pass of area-light scenes is compiled for: boxed 2.00 / 1.89 / 1.77 / 1.68 / 1.66 / 1.63 ms with 7 / 6 / 5 / 4 / 3 / 2
+#endif
 #ifndef FRAY_WAVE_SHADOW_MANY
 #define FRAY_WAVE_SHADOW_MANY 8 // shadow rays per lit record from which the 6-CTA build is used
 #endif
@@ -531,13 +535,13 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 	if (cfg.occTrace <= 0) {
 		cudaFuncSetAttribute(waveTraceKernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaFuncSetAttribute(waveShadowKernel<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
-		cudaFuncSetAttribute(waveShadowKernel<F, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
+		cudaFuncSetAttribute(waveShadowKernel<F, FRAY_WAVE_SHADOW_HEAVY_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaFuncSetAttribute(waveShadeKernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) flat);
 		cudaFuncSetAttribute(waveShadeKernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (flat + stack));
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occTrace, waveTraceKernel<F>, 128, flat + stack);
 		if (fused) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F, true>, 128, flat + stack);
 		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShade, waveShadeKernel<F, false>, 128, flat);
-		if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 6>, 128, flat + stack);
+		if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, FRAY_WAVE_SHADOW_HEAVY_CTAS>, 128, flat + stack);
 		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.occShadow, waveShadowKernel<F, 8>, 128, flat + stack);
 		if (cfg.occTrace < 1 || cfg.occShade < 1 || cfg.occShadow < 1) return cudaErrorLaunchOutOfResources;
 	}
@@ -550,7 +554,7 @@ template <int F> cudaError_t launchWaveFrameT(const DScene<float>& sc, WaveParam
 		}
 		waveShadeKernel<F, false><<<cfg.numSMs * cfg.occShade, 128, flat, cfg.stream>>>(sc, p);
 		if (sc.numLights > 0) {
-			if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) waveShadowKernel<F, 6><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
+			if (sc.lightSamples >= FRAY_WAVE_SHADOW_MANY) waveShadowKernel<F, FRAY_WAVE_SHADOW_HEAVY_CTAS><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
 			else waveShadowKernel<F, 8><<<cfg.numSMs * cfg.occShadow, 128, flat + stack, cfg.stream>>>(sc, p);
 		}
 	}
