@@ -1,4 +1,5 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r02t_tests.log 2>&1; tail -2 gpurun_out/r02t_tests.log
-python tools/time_configs.py --fp32 2>&1 | tee gpurun_out/r02t_all_configs_timing.log
-ncu --set full --clock-control none --import-source on -k regex:waveShadowKernel -s 1 -c 1 -f -o gpurun_out/r02t_boxed_waveShadowKernel python tools/render_once.py boxed --frames 2 > gpurun_out/ncu_x.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02t_launches_boxed.csv python tools/render_once.py boxed --frames 2 > /dev/null 2>&1
+for v in "" z3 z5 z6; do
+  if [ -n "$v" ]; then export FRAY_GPU_LIB=$PWD/fray_b200/_build/variants/libfray_gpu_$v.so; fi
+  echo "== variant ${v:-main(4)}"
+  python tools/render_once.py zaphod --frames 6 | sort -k6 -n | head -1
+done 2>&1 | tee gpurun_out/r02v_zaphod.log
