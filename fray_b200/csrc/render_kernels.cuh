@@ -110,6 +110,9 @@ template <typename R, int F> __device__ __forceinline__ FlatTab stageFlat(const 
 }
 
 // resident CTAs per SM the Whitted kernels with a generic node loop (KD walks: latency-bound) are compiled for
+#ifndef FRAY_GI_FLAT_CTAS
+#define FRAY_GI_FLAT_CTAS 7 // the untextured table-only path tracers (cornell_box, smallpt)
+#endif
 #ifndef FRAY_WHITTED_FLAT_CTAS
 #define FRAY_WHITTED_FLAT_CTAS 4 // the table-only Whitted kernel (zaphod)
 #endif
@@ -130,7 +133,7 @@ template <> struct RenderRng<true> {
 };
 
 template <typename R, bool GI, int F>
-__global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F_NODES | FRAY_F_TEX)) == 0) ? 7 : 6) : ((F & FRAY_F_NODES) ? FRAY_WHITTED_KD_CTAS : FRAY_WHITTED_FLAT_CTAS))) renderKernel(const DScene<R> sc, const RenderParams p)
+__global__ void __launch_bounds__(128, Num<R>::kExact ? 1 : (GI ? (((F & (FRAY_F_NODES | FRAY_F_TEX)) == 0) ? FRAY_GI_FLAT_CTAS : 6) : ((F & FRAY_F_NODES) ? FRAY_WHITTED_KD_CTAS : FRAY_WHITTED_FLAT_CTAS))) renderKernel(const DScene<R> sc, const RenderParams p)
 {
 	const FlatTab ft = stageFlat<R, F>(sc);
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
