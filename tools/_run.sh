@@ -1,6 +1,4 @@
-for v in "" g5 g6 g8; do
-  if [ -n "$v" ]; then export FRAY_GPU_LIB=$PWD/fray_b200/_build/variants/libfray_gpu_$v.so; fi
-  echo "== variant ${v:-main(7)}"
-  python tools/render_once.py cornell_box pathsPerPixel=256 --frames 5 | sort -k6 -n | head -1
-  python tools/render_once.py smallpt pathsPerPixel=256 --frames 4 | sort -k6 -n | head -1
-done 2>&1 | tee gpurun_out/r02x_gi.log
+python -m pytest tests -m gpu -x -q > gpurun_out/r02y_tests.log 2>&1; tail -2 gpurun_out/r02y_tests.log
+python tools/render_once.py boxed --frames 6 | sort -k6 -n | head -1
+python tools/render_once.py forest frameWidth=3840 frameHeight=2160 --frames 5 | sort -k6 -n | head -1
+python tools/render_once.py hw9/dragon --frames 5 | sort -k6 -n | head -1
