@@ -36,6 +36,9 @@ namespace fray {
 #define FRAY_WAVE_MAX 16     // waves per frame the counters are laid out for (maxTraceDepth + 2 must fit)
 #define FRAY_WAVE_REGIONS 64 // sub-queues per queue (power of two)
 #define FRAY_WAVE_CTR_STRIDE 32 // words between two sub-queue counters (128 bytes: another L2 line, another slice)
+#ifndef FRAY_WAVE_SHADE_CTAS
+#define FRAY_WAVE_SHADE_CTAS 6 // resident CTAs per SM of the shade pass (5 and 7 measured: see DESIGN)
+#endif
 #define FRAY_WAVE_STRIPES 16    // interleaved work counters per launch (power of two)
 
 // indices into WaveParams::ctr
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(128, FRAY_WAVE_TRACE_CTAS) waveTraceKernel(con
 // instructions): forest 4K 1.51 -> 1.66 ms, with AA 6.93 -> 7.51 ms, dragon 4.74 -> 4.78 ms. Kept as a measured alternative
 // (FRAY_GPU_FUSE=1); three passes are the default.
 template <int F, bool FUSED>
-__global__ void __launch_bounds__(128, 6) waveShadeKernel(const DScene<float> sc, const WaveParams p)
+__global__ void __launch_bounds__(128, FRAY_WAVE_SHADE_CTAS) waveShadeKernel(const DScene<float> sc, const WaveParams p)
 {
 	const FlatTab ft = stageFlat<float, F>(sc);
 	__shared__ unsigned prefix[FRAY_WAVE_REGIONS + 1];
