@@ -379,3 +379,28 @@ def test_fp32_primary_hit_ids_differ_only_at_audited_edge_ties(name, settings, d
     assert all(r[4] for r in rows), [r for r in rows if not r[4]][:10]
     hit = (waov[..., 0] >= 0) & (gaov[..., 0] == waov[..., 0]) & (gaov[..., 1] == waov[..., 1])
     np.testing.assert_allclose(gaov[..., 2][hit], waov[..., 2][hit], rtol=2e-4)
+
+
+@pytest.mark.parametrize("settings", [dict(pathsPerPixel=300), dict(pathsPerPixel=40, frameWidth=400, frameHeight=400), dict(pathsPerPixel=19, frameWidth=256, frameHeight=192)])
+def test_frame_does_not_depend_on_the_chunk_list(settings, data_dir, monkeypatch):
+    """The persistent path tracer cuts a pixel's samples into chunks of descending size (fray_gpu.cu: buildChunks -- 8 ... 1,
+    all sizes doubled until the list fits: 300 paths on a small frame, 40 on the headline frame's 160000 pixels, an odd count).
+    A sample is a pure function of (seed, pixel, sample index), so whatever the list -- here against uniform chunks of 1 and of
+    5 -- the rays are the same one for one and the frame differs by FP32 regrouping of a pixel's partial sums only."""
+    from fray_b200 import scenes as sc_mod
+    sc = fb.Scene(sc_mod.override_scene("cornell_box", "chunks", settings))
+    ctx = fb.GpuContext(sc, 0, fb.FP32)
+    monkeypatch.delenv("FRAY_GPU_CHUNK", raising=False)
+    want, ws = ctx.render(seed=11)
+    again, _ = ctx.render(seed=11)
+    assert np.array_equal(want, again)  # bit-identical run to run
+    for c in ("1", "5"):
+        monkeypatch.setenv("FRAY_GPU_CHUNK", c)
+        got, gs = ctx.render(seed=11)
+        assert gs.rays == ws.rays and gs.shadow_rays == ws.shadow_rays
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-6)
+    monkeypatch.delenv("FRAY_GPU_CHUNK", raising=False)
+    parts = [ctx.render(seed=11, flags=fb.FRAME_SUM, sample_begin=a, sample_end=b) for a, b in ((0, 7), (7, sc.spp))]
+    np.testing.assert_allclose((parts[0][0] + parts[1][0]) / sc.spp, want, rtol=2e-5, atol=1e-6)
+    assert parts[0][1].rays + parts[1][1].rays == ws.rays
+    ctx.close()
