@@ -37,7 +37,7 @@ namespace fray {
 #define FRAY_WAVE_REGIONS 64 // sub-queues per queue (power of two)
 #define FRAY_WAVE_CTR_STRIDE 32 // words between two sub-queue counters (128 bytes: another L2 line, another slice)
 #ifndef FRAY_WAVE_SHADE_CTAS
-#define FRAY_WAVE_SHADE_CTAS 6 // resident CTAs per SM of the shade pass (5 and 7 measured: see DESIGN)
+#define FRAY_WAVE_SHADE_CTAS 7 // resident CTAs per SM of the shade pass (72 registers): forest 4K -2 % against 6, which beat 4, 5 and 8
 #endif
 #define FRAY_WAVE_STRIPES 16    // interleaved work counters per launch (power of two)
 
